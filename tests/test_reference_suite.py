@@ -1,0 +1,49 @@
+"""Run the reference's OWN test files, unchanged, with the oracle standing in
+for the compiled NTL extension.  Only possible where /root/reference exists
+(the authoring container); skipped elsewhere.  This is the strongest pin on
+the oracle short of NTL itself: the reference's encoders, decoders,
+IncrementalDecoder, batch_reconstruct, randousha and refinement programs all
+run on top of it."""
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import ref_shim  # noqa: E402
+
+FILES = [
+    "tests/test_ntl.py",
+    "tests/test_reed_solomon.py",
+    "tests/test_reed_solomon_wb.py",
+    "tests/test_polynomial.py",
+    "tests/test_batch_reconstruction.py",
+    "tests/test_offline_randousha.py",
+    "tests/test_mpc.py",
+    "tests/progs/test_random_refinement.py",
+    "tests/progs/test_triple_refinement.py",
+]
+# Not about this path: pypairing (Rust) fixtures; and two tests that rely on
+# Python 3.7 cancellation semantics (UnboundLocalError in the reference's own
+# batch_reconstruction.py:183 on Python >= 3.8).
+DESELECT = ["rust", "reconstruction_timeout"]
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_reference_tests_pass_on_oracle():
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "pytest.ini"), "w") as fh:
+            fh.write("[pytest]\n")
+        env = dict(os.environ, PYTHONPATH=os.path.join(HERE, "golden"), HBMPC_NTL_IMPL="oracle")
+        cmd = [sys.executable, "-m", "pytest", "-c", os.path.join(tmp, "pytest.ini"),
+               "--rootdir", tmp, "-p", "ref_plugin", "-p", "no:cacheprovider", "-q",
+               "-k", " and ".join(f"not {d}" for d in DESELECT)]
+        cmd += [os.path.join(ref_shim.REFERENCE_ROOT, f) for f in FILES]
+        res = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
+        tail = res.stdout[-2000:] + res.stderr[-2000:]
+        assert res.returncode == 0, tail
+        assert " passed" in res.stdout and "failed" not in res.stdout.splitlines()[-1], tail
