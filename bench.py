@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Headline benchmark: GF(p) share reconstructions/sec at n=16, t=5
+(BASELINE.json configs[1]: NTT encode + interpolate, batch = 65 536 polynomials
+of t+1 = 6 shares each, BLS12-381 scalar field, synthetic random shares).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch:
+    encode      c[batch][6]  --NTT-16-->  e[batch][16]     (fft_batch_evaluate)
+    interpolate y[batch][6]  ---------->  r[batch][6]      (fft_batch_interpolate)
+    (N > 1)     all-gather of r over NCCL
+`value` counts opened shares: batch * (t+1) per step per GPU (every recovered
+coefficient is one reconstructed secret, batch_reconstruction.py:117,158).
+
+Prints ONE JSON line (see the task contract): value, roofline (dominant kernel,
+CUDA-event timed), e2e (C-ABI with pinned HOST buffers, copies inside the timed
+region), cpu_baseline (oracle/cpu_ref.cpp on this box's cores), clocks.
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+N_PARTIES, T = 16, 5
+K = T + 1
+ZS = [1, 3, 4, 9, 12, 15]  # the scattered z set of SURVEY.md section 8(d)
+METRIC = "GF(p) share reconstructions/sec at n=16,t=5"
+UNIT = "shares/s"
+E = 32  # bytes per field element
+
+
+def synth(batch, width, seed):
+    """uniform in [0, 2^254) subset of [0, p): canonical residues as uint64[batch,width,4]"""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2 ** 63, size=(batch, width, 4), dtype=np.uint64) * np.uint64(2) + \
+        rng.integers(0, 2, size=(batch, width, 4), dtype=np.uint64)
+    a[:, :, 3] >>= np.uint64(2)
+    return a
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_run(batch, steps, warmup, threads=0):
+    """The CPU restatement of the reference's NTL path (oracle/cpu_ref.cpp) on the
+    same workload; returns (shares/s, seconds per step, threads used)."""
+    import numpy as np
+
+    import __graft_entry__ as graft
+    from oracle import cpu_ref
+    from oracle import hbmpc_oracle as orc
+
+    graft.build_oracle()
+    ref = cpu_ref.CpuRef()
+    pt = orc.EvalPoint(P, N_PARTIES, True)
+    c = synth(batch, K, 0xB202)
+    enc = ref.fft_batch_evaluate_limbs(c, pt.omega, P, pt.order, N_PARTIES, threads=threads)
+    y = np.ascontiguousarray(enc[:, ZS, :])
+    for _ in range(warmup):
+        ref.fft_batch_evaluate_limbs(c, pt.omega, P, pt.order, N_PARTIES, threads=threads)
+        ref.fft_batch_interpolate_limbs(ZS, y, pt.omega, P, pt.order, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.fft_batch_evaluate_limbs(c, pt.omega, P, pt.order, N_PARTIES, threads=threads)
+        r = ref.fft_batch_interpolate_limbs(ZS, y, pt.omega, P, pt.order, threads=threads)
+    dt = (time.perf_counter() - t0) / steps
+    assert np.array_equal(r, c), "CPU reference round trip failed"
+    used = threads if threads > 0 else ref.max_threads()
+    return batch * K / dt, dt, used
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8192
+    steps = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 3))
+    value, dt, cores = cpu_reference_run(sample, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 mod p",
+        "data": "synthetic",
+        "config": {"workload": "n=16 t=5 NTT encode+interpolate (BASELINE configs[1])",
+                   "batch_polys_per_step": sample, "shares_per_poly": K, "field": "BLS12-381 r"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} polynomials x {steps} steps; C++ restatement of "
+                                   "rsdecode_impl.h (NTL itself is not installable here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from honeybadgermpc_b200 import _native
+    from honeybadgermpc_b200.field import GF
+    from honeybadgermpc_b200.ntl import pack_vec
+    from honeybadgermpc_b200.polynomial import EvalPoint
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    batch, sets = args.batch, args.sets
+    pt = EvalPoint(GF(P), N_PARTIES, True)
+    omega = pack_vec([pt.omega.value], P)[0]
+    ctx = _native.Context(P, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    def dev_u64(a):
+        return torch.from_numpy(a.view(np.int64)).to(dev)
+
+    # ---- synthetic inputs, resident in HBM; `sets` rotating buffer sets so every
+    # step reads cold data (sets * 71 MB >> 126 MB of L2)
+    c, e, y, r = [], [], [], []
+    zs_t = torch.tensor(ZS, device=dev)
+    with torch.cuda.stream(stream):
+        for s in range(sets):
+            cs = dev_u64(synth(batch, K, 0xB202 + 977 * s + 131 * rank))
+            es = torch.empty((batch, N_PARTIES, 4), dtype=torch.int64, device=dev)
+            ctx.fft_batch_evaluate(omega, pt.order, cs.data_ptr(), batch, K, N_PARTIES,
+                                   es.data_ptr(), _native.MEM_DEVICE)
+            ys = es.index_select(1, zs_t).contiguous()
+            es.zero_()
+            c.append(cs)
+            e.append(es)
+            y.append(ys)
+            r.append(torch.zeros((batch, K, 4), dtype=torch.int64, device=dev))
+        gathered = torch.empty((world * batch, K, 4), dtype=torch.int64, device=dev) if world > 1 else None
+    stream.synchronize()
+
+    def step(s, evs=None):
+        if evs is not None:
+            evs[0].record(stream)
+        ctx.fft_batch_evaluate(omega, pt.order, c[s].data_ptr(), batch, K, N_PARTIES,
+                               e[s].data_ptr(), _native.MEM_DEVICE)
+        if evs is not None:
+            evs[1].record(stream)
+        ctx.fft_batch_interpolate(omega, pt.order, ZS, y[s].data_ptr(), batch, r[s].data_ptr(),
+                                  _native.MEM_DEVICE)
+        if evs is not None:
+            evs[2].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, r[s])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i % sets)
+        barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = ctx.launch_count()
+        barrier()
+        t_start.record(stream)
+        for i in range(args.steps):
+            step((args.warmup + i) % sets, evs[i])
+        t_end.record(stream)
+        barrier()
+        launches = ctx.launch_count() - launches0
+        sampler.stop_flag.set()
+        sampler.join()
+    total_ms = t_start.elapsed_time(t_end)
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / args.steps
+    dec_ms = sum(ev[1].elapsed_time(ev[2]) for ev in evs) / args.steps
+
+    # parity inside the bench: every decoded block equals its coefficients
+    for s in range(min(sets, args.warmup + args.steps)):
+        assert torch.equal(r[s], c[s]), f"round trip mismatch in buffer set {s}"
+    if world > 1:
+        last = (args.warmup + args.steps - 1) % sets
+        assert torch.equal(gathered[rank * batch:(rank + 1) * batch], r[last])
+
+    ms_per_step = total_ms / args.steps
+    value = world * batch * K / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes)
+    enc_bytes = batch * (K + N_PARTIES) * E
+    dec_bytes = batch * (K + K) * E
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    if enc_ms >= dec_ms:
+        dom, dom_ms, dom_bytes = "encode: " + args.encode_kernel, enc_ms, enc_bytes
+    else:
+        dom, dom_ms, dom_bytes = "interpolate: apply_matrix_kernel", dec_ms, dec_bytes
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(dom.split(": ")[1])
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "kernel": dom, "peak_source": peak_src,
+                "kernel_ms": {"encode": enc_ms, "interpolate": dec_ms},
+                "step_GBps": (enc_bytes + dec_bytes) / (ms_per_step * 1e-3) / 1e9,
+                "note": "integer-pipe (IMAD.WIDE) bound, see DESIGN.md section 4"}
+
+    # ---- end to end: the C-ABI call a reference-side binding makes, HOST buffers
+    # (pinned), H2D + kernel + D2H inside the timed region
+    e2e_steps = max(3, min(args.steps, 20))
+    hc = torch.from_numpy(synth(batch, K, 0xE2E + rank).view(np.int64)).pin_memory()
+    he = torch.empty((batch, N_PARTIES, 4), dtype=torch.int64).pin_memory()
+    hy = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
+    hr = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        ctx.fft_batch_evaluate(omega, pt.order, hc.data_ptr(), batch, K, N_PARTIES, he.data_ptr(),
+                               _native.MEM_HOST)
+        ctx.fft_batch_interpolate(omega, pt.order, ZS, hy.data_ptr(), batch, hr.data_ptr(),
+                                  _native.MEM_HOST)
+
+    e2e_step()
+    hy.copy_(he[:, ZS, :])
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    assert torch.equal(hr, hc), "end-to-end round trip mismatch"
+    if world > 1:
+        tt = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_dt = float(tt.item())
+    e2e = {"value": world * batch * K / e2e_dt, "unit": UNIT,
+           "h2d_bytes_per_step": 2 * batch * K * E,
+           "d2h_bytes_per_step": batch * (N_PARTIES + K) * E,
+           "ms_per_step": e2e_dt * 1e3,
+           "boundary": "hbg_fft_batch_evaluate + hbg_fft_batch_interpolate, HBG_MEM_HOST, pinned buffers"}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            sample = 16384
+            v, dt, cores = cpu_reference_run(sample, 12, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{sample} polynomials x 12 steps of the same encode+interpolate; "
+                             "oracle/cpu_ref.cpp (C++ restatement of rsdecode_impl.h, OpenMP over the batch)",
+                   "ms_per_step": dt * 1e3}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 Montgomery (256-bit integer mod p)",
+            "data": "synthetic",
+            "config": {"workload": "n=16 t=5 NTT encode+interpolate (BASELINE configs[1])",
+                       "batch_polys_per_gpu": batch, "shares_per_poly": K,
+                       "field": "BLS12-381 r", "z": ZS,
+                       "l2": f"{sets} rotating buffer sets of {(enc_bytes + dec_bytes) / 1e6:.0f} MB "
+                             "(inputs+outputs larger than the 126 MB L2)",
+                       "parallelism": f"batch shard x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                       "polys_per_s": value / K},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": sampler.result(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--sets", type=int, default=6)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--encode-kernel", default="ntt_smem_kernel")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,8 @@ struct FieldBLS {
   // p = 1 (mod 2^32) and p[1] = 2^32-1: the two lowest columns of m*p are
   // adds/subs of m, not multiplies (see redc_row_low_ones).
   static constexpr bool kLowOnes = true;
+  // macs between two acc_fold calls: p*R + 2*p^2 < 2^512 for this p
+  static constexpr int kFold = 2;
 };
 
 // Same field, but the limbs come from the constant bank instead of immediates
@@ -67,11 +69,13 @@ struct FieldAny {
   static HB_D uint32_t p(int i) { return c_field.p[i]; }
   static HB_D uint32_t n0inv() { return c_field.n0inv; }
   static constexpr bool kLowOnes = false;
+  static constexpr int kFold = 1;
 };
 struct FieldBLSConst {
   static HB_D uint32_t p(int i) { return c_field.p[i]; }
   static HB_D uint32_t n0inv() { return 0xffffffffu; }
   static constexpr bool kLowOnes = true;
+  static constexpr int kFold = 2;
 };
 #endif
 
@@ -85,6 +89,7 @@ struct FieldHost {
   static inline uint32_t p(int i) { return cur()->p[i]; }
   static inline uint32_t n0inv() { return cur()->n0inv; }
   static constexpr bool kLowOnes = false;
+  static constexpr int kFold = 1;
 };
 // Host twin of the BLS fast reduction (unit tests only).
 struct FieldHostLowOnes : FieldHost {
@@ -384,6 +389,88 @@ HB_HD Fe mont_mul(const Fe& a, const Fe& b) {
   for (int i = 0; i < 7; i++) hi[i] = y[i + 1];
   hi[7] = 0;
   add8(r.w, x, hi);
+  cond_sub_p<F>(r);
+  return r;
+}
+
+
+// ---------------------------------------------------------------------------
+// Lazy-reduction dot products.  A row dot product sum_j a_j*b_j is accumulated
+// as a 512-bit integer and Montgomery-reduced ONCE (instead of once per
+// product): 64 IMAD.WIDE per term + 64 (48 for BLS) per output.
+//
+// Representation: value = w[0..16) + sum_i k[i] * 2^(32*(8+i)).  The k words
+// are deferred carries: every 4-product chain that ends at word t >= 8 drops
+// its carry-out into k[t-8] instead of rippling upwards, so each chain is one
+// short asm statement.  Only words >= 8 ever receive deferred carries, and the
+// Montgomery quotient digits depend on words < 8 only, so deferral is exact.
+// ---------------------------------------------------------------------------
+struct Acc {
+  uint32_t w[16];
+  uint32_t k[8];
+};
+
+HB_HD void acc_zero(Acc& t) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) t.w[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.k[i] = 0;
+}
+
+// t += a*b.  Caller keeps the true value below 2^512 (see acc_fold).
+HB_HD void acc_mac(Acc& t, const Fe& a, const Fe& b) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    cmad4_top(t.w + i, t.k[i], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
+    if (i < 7) {
+      cmad4_top(t.w + i + 1, t.k[i + 1], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+    } else {
+      cmad4(t.w + 8, a.w[1], a.w[3], a.w[5], a.w[7], b.w[7]);  // top chain: no carry out (< 2^512)
+    }
+  }
+}
+
+// Resolve the deferred carries and bring the value below p*2^256 by one
+// conditional subtraction of p*2^256.  Precondition: value < 2*p*2^256 and
+// < 2^512.  With inputs a < p, b < p each product is < p^2 < 0.46*p*2^256, so
+// for the BLS field (p ~ 0.453*2^256) one fold per TWO macs keeps both bounds:
+// p*R + 2*p^2 < 2^512 * 0.87.  Generic fields fold after every mac
+// (p*R + p^2 < 2*p*R always; < 2^512 needs p < 2^255, else the host rejects).
+template <class F>
+HB_HD void acc_fold(Acc& t) {
+  uint32_t p[8], hi[8], d[8];
+  load_p<F>(p);
+  add8(hi, t.w + 8, t.k);
+  uint32_t borrow = sub8(d, hi, p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    t.w[8 + i] = borrow ? hi[i] : d[i];
+    t.k[i] = 0;
+  }
+}
+
+// Montgomery reduction of a folded accumulator (value < p*2^256): value/R mod p,
+// canonical.
+template <class F>
+HB_HD Fe acc_redc(Acc& t) {
+  uint32_t p[8];
+  load_p<F>(p);
+  const uint32_t n0 = F::n0inv();
+  uint32_t k[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) k[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t m = t.w[i] * n0;
+    cmad4_top(t.w + i, k[i], p[0], p[2], p[4], p[6], m);
+    if (i < 7) {
+      cmad4_top(t.w + i + 1, k[i + 1], p[1], p[3], p[5], p[7], m);
+    } else {
+      cmad4(t.w + 8, p[1], p[3], p[5], p[7], m);  // total < 2*p*2^256 < 2^512
+    }
+  }
+  Fe r;
+  add8(r.w, t.w + 8, k);
   cond_sub_p<F>(r);
   return r;
 }

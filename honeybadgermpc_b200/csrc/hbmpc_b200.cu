@@ -1,0 +1,540 @@
+// C-ABI of libhbmpc_b200.so (see include/hbmpc_b200.h): context, constant
+// cache, staging of host buffers, kernel launches.  Host code here derives the
+// O(n^2) per-point-set constants only; every batch element is touched by CUDA
+// kernels exclusively.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hbmpc_b200.h"
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+using namespace hb;
+
+#define HBG_STR2(x) #x
+#define HBG_STR(x) HBG_STR2(x)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct DevConst {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct hbg_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  FieldParams fp;
+  HostField* field = nullptr;
+  bool is_bls = false;
+  int fft_path = 0;  // 0 auto, 1 matrix, 2 ntt
+  std::string err;
+  uint64_t launches = 0;
+  const char* last_kernel = "";
+  DevBuf in, out, work;
+  std::unordered_map<std::string, DevConst> cache;
+  size_t cache_bytes = 0;
+};
+
+namespace {
+
+std::mutex g_field_mutex;
+struct DeviceFieldState {
+  bool valid = false;
+  FieldParams fp;
+};
+DeviceFieldState g_dev_field[64];
+
+int fail(hbg_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(ctx, HBG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// FieldAny kernels read the modulus from the __constant__ bank of this module.
+int bind_field(hbg_ctx* ctx) {
+  if (ctx->is_bls) return HBG_OK;  // FieldBLS: immediates
+  std::lock_guard<std::mutex> lk(g_field_mutex);
+  DeviceFieldState& st = g_dev_field[ctx->device];
+  if (st.valid && memcmp(&st.fp, &ctx->fp, sizeof(FieldParams)) == 0) return HBG_OK;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyToSymbol(c_field, &ctx->fp, sizeof(FieldParams)));
+  CU(cudaDeviceSynchronize());
+  st.valid = true;
+  st.fp = ctx->fp;
+  return HBG_OK;
+}
+
+int ensure(hbg_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return HBG_OK;
+  if (b.p) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMalloc(&b.p, cap);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(ctx, HBG_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  b.cap = cap;
+  return HBG_OK;
+}
+
+// Cached device constant; `build` fills the host bytes when the key is new.
+template <class Build>
+int get_const(hbg_ctx* ctx, const std::string& key, const void** out, Build build) {
+  auto it = ctx->cache.find(key);
+  if (it != ctx->cache.end()) {
+    *out = it->second.p;
+    return HBG_OK;
+  }
+  std::vector<uint32_t> host;
+  int rc = build(host);
+  if (rc != HBG_OK) return rc;
+  if (ctx->cache_bytes > (256u << 20)) {  // bound the cache: drop everything
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& kv : ctx->cache) cudaFree(kv.second.p);
+    ctx->cache.clear();
+    ctx->cache_bytes = 0;
+  }
+  DevConst dc;
+  dc.bytes = host.size() * 4;
+  CU(cudaMalloc(&dc.p, dc.bytes ? dc.bytes : 4));
+  CU(cudaMemcpyAsync(dc.p, host.data(), dc.bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // host vector dies at scope exit
+  ctx->cache[key] = dc;
+  ctx->cache_bytes += dc.bytes;
+  *out = dc.p;
+  return HBG_OK;
+}
+
+std::string make_key(const char* tag, const void* a, size_t na, const void* b = nullptr,
+                     size_t nb = 0, int x = 0, int y = 0) {
+  std::string k(tag);
+  k.append((const char*)&x, sizeof x);
+  k.append((const char*)&y, sizeof y);
+  k.append((const char*)a, na);
+  if (b) k.append((const char*)b, nb);
+  return k;
+}
+
+// Points in standard form -> Montgomery form; rejects non-canonical values.
+int load_points(hbg_ctx* ctx, const uint64_t* xs, int n, std::vector<Fe>& out) {
+  out.resize(n);
+  Fe p;
+  memcpy(p.w, ctx->fp.p, 32);
+  for (int i = 0; i < n; i++) {
+    Fe v = fe_from_u64(xs + 4 * i);
+    if (fe_cmp(v, p) >= 0) return fail(ctx, HBG_ERR_INVALID, "evaluation point not in [0, p)");
+    out[i] = ctx->field->to_mont(v);
+  }
+  return HBG_OK;
+}
+
+// Row-major (rows x cols) matrix -> [col][word][row] interleaved words.
+void interleave(const std::vector<Fe>& m, int rows, int cols, std::vector<uint32_t>& out) {
+  out.assign((size_t)rows * cols * 8, 0);
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++)
+      for (int w = 0; w < 8; w++)
+        out[((size_t)j * 8 + w) * rows + i] = m[(size_t)i * cols + j].w[w];
+}
+
+struct Staged {
+  const void* d_in = nullptr;
+  void* d_out = nullptr;
+};
+
+int stage(hbg_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes, int mem,
+          Staged& s) {
+  if (mem == HBG_MEM_DEVICE) {
+    s.d_in = in;
+    s.d_out = out;
+    return HBG_OK;
+  }
+  if (mem != HBG_MEM_HOST) return fail(ctx, HBG_ERR_INVALID, "mem must be HBG_MEM_HOST or HBG_MEM_DEVICE");
+  int rc = ensure(ctx, ctx->in, in_bytes);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->out, out_bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  s.d_in = ctx->in.p;
+  s.d_out = ctx->out.p;
+  return HBG_OK;
+}
+
+int unstage(hbg_ctx* ctx, void* out, size_t out_bytes, int mem) {
+  if (mem == HBG_MEM_DEVICE) return HBG_OK;
+  CU(cudaMemcpyAsync(out, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HBG_OK;
+}
+
+int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_in, int in_stride,
+                  void* d_out, int out_stride, size_t batch) {
+  MatvecArgs a;
+  a.mt = (const uint32_t*)mt;
+  a.in = (const uint4*)d_in;
+  a.out = (uint4*)d_out;
+  a.in_cols = nullptr;
+  a.batch = batch;
+  a.n_out = n_out;
+  a.d = d;
+  a.in_stride = in_stride;
+  a.out_stride = out_stride;
+  unsigned long long total = (unsigned long long)batch * n_out;
+  unsigned long long blocks = (total + 255) / 256;
+  if (blocks == 0) return HBG_OK;
+  if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
+  int rc = bind_field(ctx);
+  if (rc) return rc;
+  if (ctx->is_bls)
+    apply_matrix_kernel<FieldBLS><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+  else
+    apply_matrix_kernel<FieldAny><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "apply_matrix_kernel";
+  return HBG_OK;
+}
+
+int ilog2(int n) {
+  int l = 0;
+  while ((1 << l) < n) l++;
+  return l;
+}
+
+int check_omega(hbg_ctx* ctx, const uint64_t omega[4], int n, Fe& w_mont) {
+  if (n < 1 || (n & (n - 1)) != 0) return fail(ctx, HBG_ERR_INVALID, "fft size must be a power of two");
+  std::vector<Fe> w;
+  int rc = load_points(ctx, omega, 1, w);
+  if (rc) return rc;
+  w_mont = w[0];
+  const HostField& f = *ctx->field;
+  if (n == 1) return HBG_OK;
+  Fe half = f.pow_u64(w_mont, (uint64_t)n / 2);
+  Fe minus_one = f.neg(f.one());
+  if (!fe_eq(half, minus_one))
+    return fail(ctx, HBG_ERR_INVALID, "omega is not a primitive n-th root of unity");
+  return HBG_OK;
+}
+
+int twiddles(hbg_ctx* ctx, const uint64_t omega[4], const Fe& w_mont, int n, const void** d_tw) {
+  std::string key = make_key("tw", omega, 32, nullptr, 0, n);
+  return get_const(ctx, key, d_tw, [&](std::vector<uint32_t>& host) {
+    int half = n / 2 > 0 ? n / 2 : 1;
+    host.resize((size_t)half * 8);
+    Fe acc = ctx->field->one();
+    for (int i = 0; i < half; i++) {
+      memcpy(&host[(size_t)i * 8], acc.w, 32);
+      acc = ctx->field->mul(acc, w_mont);
+    }
+    return HBG_OK;
+  });
+}
+
+int launch_ntt(hbg_ctx* ctx, const void* d_tw, int n, const void* d_in, int d, void* d_out,
+               int k_out, size_t batch) {
+  int rc = bind_field(ctx);
+  if (rc) return rc;
+  int log_n = ilog2(n);
+  if (n <= 1024) {
+    NttArgs a;
+    a.in = (const uint4*)d_in;
+    a.out = (uint4*)d_out;
+    a.tw = (const uint4*)d_tw;
+    a.batch = batch;
+    a.n = n;
+    a.log_n = log_n;
+    a.d = d;
+    a.k_out = k_out;
+    int per_cta = n >= 512 ? 1 : 512 / n;
+    size_t blocks = (batch + per_cta - 1) / per_cta;
+    if (blocks == 0) return HBG_OK;
+    if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
+    size_t smem = (size_t)per_cta * n * 32;
+    if (ctx->is_bls)
+      ntt_smem_kernel<FieldBLS><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+    else
+      ntt_smem_kernel<FieldAny><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_kernel = "ntt_smem_kernel";
+    return HBG_OK;
+  }
+  // large n: scatter, one pass per stage, gather
+  rc = ensure(ctx, ctx->work, (size_t)batch * n * 32);
+  if (rc) return rc;
+  NttBigArgs a;
+  a.work = (uint4*)ctx->work.p;
+  a.in = (const uint4*)d_in;
+  a.out = (uint4*)d_out;
+  a.tw = (const uint4*)d_tw;
+  a.batch = batch;
+  a.n = n;
+  a.log_n = log_n;
+  a.d = d;
+  a.k_out = k_out;
+  a.stage = 0;
+  unsigned long long tot = (unsigned long long)batch * n;
+  if ((tot + 255) / 256 > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch*n too large");
+  ntt_big_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  for (int s = 1; s <= log_n; s++) {
+    a.stage = s;
+    unsigned blocks = (unsigned)((tot / 2 + 255) / 256);
+    if (ctx->is_bls)
+      ntt_big_stage_kernel<FieldBLS><<<blocks, 256, 0, ctx->stream>>>(a);
+    else
+      ntt_big_stage_kernel<FieldAny><<<blocks, 256, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
+  unsigned long long otot = (unsigned long long)batch * k_out;
+  if (otot) {
+    ntt_big_gather_kernel<<<(unsigned)((otot + 255) / 256), 256, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
+  ctx->last_kernel = "ntt_big_stage_kernel";
+  return HBG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hbg_version(void) { return "hbmpc_b200 0.1 (sm_100a, 8x32 Montgomery, CUDA " HBG_STR(CUDART_VERSION) ")"; }
+
+int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
+  if (!out || !modulus) return HBG_ERR_INVALID;
+  *out = nullptr;
+  FieldParams fp;
+  if (!field_params_init(modulus, &fp)) return HBG_ERR_INVALID;
+  if (modulus[3] >> 63) return HBG_ERR_UNSUPPORTED;  // lazy-reduction bounds need p < 2^255
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count || device >= 64)
+    return HBG_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return HBG_ERR_CUDA;
+  hbg_ctx* ctx = new hbg_ctx();
+  ctx->device = device;
+  ctx->fp = fp;
+  ctx->field = new HostField(fp);
+  ctx->is_bls = true;
+  for (int i = 0; i < 8; i++) ctx->is_bls = ctx->is_bls && fp.p[i] == FieldBLS::p(i);
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx->field;
+    delete ctx;
+    return HBG_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return HBG_OK;
+}
+
+void hbg_ctx_destroy(hbg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->cache) cudaFree(kv.second.p);
+  if (ctx->in.p) cudaFree(ctx->in.p);
+  if (ctx->out.p) cudaFree(ctx->out.p);
+  if (ctx->work.p) cudaFree(ctx->work.p);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx->field;
+  delete ctx;
+}
+
+const char* hbg_ctx_last_error(const hbg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int hbg_ctx_set_stream(hbg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return HBG_ERR_INVALID;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return HBG_OK;
+}
+
+int hbg_ctx_synchronize(hbg_ctx* ctx) {
+  if (!ctx) return HBG_ERR_INVALID;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HBG_OK;
+}
+
+uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
+
+int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path) {
+  if (!ctx || path < 0 || path > 2) return HBG_ERR_INVALID;
+  ctx->fft_path = path;
+  return HBG_OK;
+}
+
+int hbg_vandermonde_batch_evaluate(hbg_ctx* ctx, const uint64_t* xs, int n, const uint64_t* polys,
+                                   size_t batch, int d, uint64_t* out, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (n < 0 || d < 0 || (n && !xs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  if (batch == 0 || n == 0) return HBG_OK;
+  if (!out || (d && !polys)) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  CU(cudaSetDevice(ctx->device));
+  const void* d_m = nullptr;
+  int rc = get_const(ctx, make_key("vdm", xs, (size_t)n * 32, nullptr, 0, n, d), &d_m,
+                     [&](std::vector<uint32_t>& host) {
+                       std::vector<Fe> x;
+                       int r = load_points(ctx, xs, n, x);
+                       if (r) return r;
+                       std::vector<Fe> m((size_t)n * (d ? d : 1), fe_zero());
+                       for (int i = 0; i < n; i++) {  // set_vm_matrix, rsdecode_impl.h:23-36
+                         Fe acc = ctx->field->one();
+                         for (int j = 0; j < d; j++) {
+                           m[(size_t)i * d + j] = acc;
+                           acc = ctx->field->mul(acc, x[i]);
+                         }
+                       }
+                       interleave(m, n, d, host);
+                       return HBG_OK;
+                     });
+  if (rc) return rc;
+  Staged s;
+  rc = stage(ctx, polys, batch * (size_t)d * 32, out, batch * (size_t)n * 32, mem, s);
+  if (rc) return rc;
+  rc = launch_matvec(ctx, d_m, n, d, s.d_in, d, s.d_out, n, batch);
+  if (rc) return rc;
+  return unstage(ctx, out, batch * (size_t)n * 32, mem);
+}
+
+static int interp_matrix(hbg_ctx* ctx, const std::string& key, const std::vector<Fe>& x_mont,
+                         const void** d_m) {
+  int k = (int)x_mont.size();
+  return get_const(ctx, key, d_m, [&](std::vector<uint32_t>& host) {
+    std::vector<Fe> inv;
+    if (!vandermonde_inverse(*ctx->field, x_mont, inv))
+      return fail(ctx, HBG_ERR_SINGULAR, "evaluation points are not pairwise distinct");
+    interleave(inv, k, k, host);
+    return HBG_OK;
+  });
+}
+
+int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, const uint64_t* ys,
+                                      size_t batch, uint64_t* out, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (k < 0 || (k && !xs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<Fe> x;
+  int rc = load_points(ctx, xs, k, x);
+  if (rc) return rc;
+  const void* d_m = nullptr;
+  // the singularity check must run even for an empty batch (pyx:167-169)
+  rc = interp_matrix(ctx, make_key("vinv", xs, (size_t)k * 32, nullptr, 0, k), x, &d_m);
+  if (rc) return rc;
+  if (batch == 0 || k == 0) return HBG_OK;
+  if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  Staged s;
+  rc = stage(ctx, ys, batch * (size_t)k * 32, out, batch * (size_t)k * 32, mem, s);
+  if (rc) return rc;
+  rc = launch_matvec(ctx, d_m, k, k, s.d_in, k, s.d_out, k, batch);
+  if (rc) return rc;
+  return unstage(ctx, out, batch * (size_t)k * 32, mem);
+}
+
+int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const uint64_t* polys,
+                           size_t batch, int d, int k_out, uint64_t* out, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!omega || d < 0 || k_out < 0 || k_out > n)
+    return fail(ctx, HBG_ERR_INVALID, "bad size or null omega");
+  CU(cudaSetDevice(ctx->device));
+  Fe w;
+  int rc = check_omega(ctx, omega, n, w);
+  if (rc) return rc;
+  if (batch == 0 || k_out == 0) return HBG_OK;
+  if (!out || (d && !polys)) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  const int d_eff = d < n ? d : n;
+  // cost in IMAD.WIDE per polynomial: dot products vs butterflies
+  double cost_mat = (double)k_out * d_eff * 64 + 64.0 * k_out;
+  double cost_ntt = (double)(n / 2) * (ilog2(n) > 1 ? ilog2(n) - 1 : 0) * 120 + 1;
+  bool use_matrix = n < 2 || cost_mat <= cost_ntt;
+  if (ctx->fft_path == 1 && (size_t)k_out * d_eff <= (1u << 22)) use_matrix = true;
+  if (ctx->fft_path == 2 && n >= 2) use_matrix = false;
+  if ((size_t)k_out * d_eff > (1u << 22)) use_matrix = false;
+  Staged s;
+  rc = stage(ctx, polys, batch * (size_t)d * 32, out, batch * (size_t)k_out * 32, mem, s);
+  if (rc) return rc;
+  if (use_matrix) {
+    const void* d_m = nullptr;
+    rc = get_const(ctx, make_key("dft", omega, 32, nullptr, 0, k_out, d_eff), &d_m,
+                   [&](std::vector<uint32_t>& host) {
+                     std::vector<Fe> m((size_t)k_out * (d_eff ? d_eff : 1), fe_zero());
+                     Fe wi = ctx->field->one();  // omega^i
+                     for (int i = 0; i < k_out; i++) {
+                       Fe acc = ctx->field->one();
+                       for (int j = 0; j < d_eff; j++) {
+                         m[(size_t)i * d_eff + j] = acc;
+                         acc = ctx->field->mul(acc, wi);
+                       }
+                       wi = ctx->field->mul(wi, w);
+                     }
+                     interleave(m, k_out, d_eff, host);
+                     return HBG_OK;
+                   });
+    if (rc) return rc;
+    rc = launch_matvec(ctx, d_m, k_out, d_eff, s.d_in, d, s.d_out, k_out, batch);
+  } else {
+    const void* d_tw = nullptr;
+    rc = twiddles(ctx, omega, w, n, &d_tw);
+    if (rc) return rc;
+    rc = launch_ntt(ctx, d_tw, n, s.d_in, d, s.d_out, k_out, batch);
+  }
+  if (rc) return rc;
+  return unstage(ctx, out, batch * (size_t)k_out * 32, mem);
+}
+
+int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, const int32_t* zs, int k,
+                              const uint64_t* ys, size_t batch, uint64_t* out, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!omega || k < 0 || (k && !zs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  if (k > 4096) return fail(ctx, HBG_ERR_UNSUPPORTED, "interpolation from more than 4096 points");
+  CU(cudaSetDevice(ctx->device));
+  Fe w;
+  int rc = check_omega(ctx, omega, n, w);
+  if (rc) return rc;
+  std::vector<Fe> x(k);
+  for (int i = 0; i < k; i++) {
+    if (zs[i] < 0 || zs[i] >= n) return fail(ctx, HBG_ERR_INVALID, "z outside [0, n)");
+    x[i] = ctx->field->pow_u64(w, (uint64_t)zs[i]);
+  }
+  const void* d_m = nullptr;
+  rc = interp_matrix(ctx, make_key("finv", omega, 32, zs, (size_t)k * 4, n, k), x, &d_m);
+  if (rc) return rc;
+  if (batch == 0 || k == 0) return HBG_OK;
+  if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  Staged s;
+  rc = stage(ctx, ys, batch * (size_t)k * 32, out, batch * (size_t)k * 32, mem, s);
+  if (rc) return rc;
+  rc = launch_matvec(ctx, d_m, k, k, s.d_in, k, s.d_out, k, batch);
+  if (rc) return rc;
+  return unstage(ctx, out, batch * (size_t)k * 32, mem);
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Batch kernels of the share-reconstruction path (sm_100a).
+//
+// Data layout (HBM): an element is 32 bytes (8 x u32 little endian = 4 x u64),
+// canonical residue; batch arrays are dense row-major [batch][width], so one
+// polynomial's coefficients / one row of the (batch x n) share matrix is one
+// contiguous run of 128-bit vectors.  All constants (matrices, twiddles) are
+// in Montgomery form, data stays in standard form: mont_mul(data, constant)
+// is the plain product, so no conversion pass ever touches the batch.
+#pragma once
+#include "fp256.cuh"
+
+namespace hb {
+
+HB_D Fe ld_fe(const uint4* p) {
+  uint4 lo = p[0], hi = p[1];
+  Fe r;
+  r.w[0] = lo.x; r.w[1] = lo.y; r.w[2] = lo.z; r.w[3] = lo.w;
+  r.w[4] = hi.x; r.w[5] = hi.y; r.w[6] = hi.z; r.w[7] = hi.w;
+  return r;
+}
+
+HB_D void st_fe(uint4* p, const Fe& r) {
+  p[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+  p[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+}
+
+// ---------------------------------------------------------------------------
+// apply_matrix: out[b][i] = sum_j M[i][j] * in[b][col(j)]
+//
+// Serves vandermonde_batch_evaluate (M = V(x)), vandermonde_batch_interpolate
+// and fft_batch_interpolate (M = V(x)^-1), and the hyper-invertible-matrix
+// step of RanDouSha (rsdecode_impl.h:23-36, :97-122; pyx:183, :237 -- the
+// reference runs these as one NTL mat_ZZ_p mul).
+// One thread per output element; the row dot product is accumulated lazily
+// (acc_mac) and reduced once.  M is stored word-interleaved ([j][word][i]) so
+// the 32 lanes of a warp read 32 consecutive words.
+// ---------------------------------------------------------------------------
+struct MatvecArgs {
+  const uint32_t* mt;        // [d][8][n_out]
+  const uint4* in;           // [batch][in_stride] elements
+  uint4* out;                // [batch][out_stride] elements
+  const int* in_cols;        // optional gather of input columns (device), or null
+  unsigned long long batch;
+  int n_out, d;
+  int in_stride, out_stride;
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) apply_matrix_kernel(MatvecArgs a) {
+  unsigned long long g = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+  unsigned long long total = a.batch * (unsigned long long)a.n_out;
+  if (g >= total) return;
+  unsigned long long b = g / (unsigned)a.n_out;
+  int i = (int)(g - b * (unsigned)a.n_out);
+  const uint4* row = a.in + 2ull * b * (unsigned)a.in_stride;
+  const uint32_t* mcol = a.mt + i;
+  Acc acc;
+  acc_zero(acc);
+  int pending = 0;
+  for (int j = 0; j < a.d; j++) {
+    int c = a.in_cols ? a.in_cols[j] : j;
+    Fe x = ld_fe(row + 2 * c);
+    Fe m;
+#pragma unroll
+    for (int w = 0; w < 8; w++) m.w[w] = mcol[(size_t)(j * 8 + w) * a.n_out];
+    acc_mac(acc, x, m);
+    if (++pending == F::kFold) {
+      acc_fold<F>(acc);
+      pending = 0;
+    }
+  }
+  if (pending) acc_fold<F>(acc);
+  Fe r = acc_redc<F>(acc);
+  st_fe(a.out + 2ull * (b * (unsigned)a.out_stride + i), r);
+}
+
+// ---------------------------------------------------------------------------
+// Radix-2 NTT in shared memory (fft / partial_fft / fft_batch_evaluate,
+// rsdecode_impl.h:125-192).  n <= 1024.  A CTA of 256 threads transforms
+// max(1, 512/n) polynomials at a time; element planes are split in two uint4
+// halves so consecutive lanes touch consecutive 16-byte slots.
+// DIT: inputs are zero-padded to n and scattered to bit-reversed slots, the
+// first stage (all twiddles 1) skips the multiply.
+// ---------------------------------------------------------------------------
+struct NttArgs {
+  const uint4* in;     // [batch][d]
+  uint4* out;          // [batch][k_out]
+  const uint4* tw;     // [n/2] omega^i, Montgomery form
+  unsigned long long batch;
+  int n, log_n, d, k_out;
+};
+
+HB_D Fe lds_fe(const uint4* lo, const uint4* hi, int e) {
+  uint4 a = lo[e], b = hi[e];
+  Fe r;
+  r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+  r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  return r;
+}
+
+HB_D void sts_fe(uint4* lo, uint4* hi, int e, const Fe& r) {
+  lo[e] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+  hi[e] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) ntt_smem_kernel(NttArgs a) {
+  extern __shared__ uint4 smem[];
+  const int n = a.n, log_n = a.log_n;
+  const int per_cta = n >= 512 ? 1 : 512 / n;
+  const int elems = per_cta * n;
+  uint4* lo = smem;
+  uint4* hi = smem + elems;
+  const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+  const int d = a.d < n ? a.d : n;  // coefficients beyond n are dropped (rsdecode_impl.h:173-175)
+
+  // load + bit-reverse scatter (one uint4 half per step: fully coalesced)
+  for (int q = threadIdx.x; q < 2 * elems; q += 256) {
+    int e = q >> 1, half = q & 1;
+    int poly = e / n, j = e - poly * n;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (j < d && first + poly < a.batch) v = a.in[2ull * ((first + poly) * a.d + j) + half];
+    int rj = (int)(__brev((unsigned)j) >> (32 - log_n));
+    (half ? hi : lo)[poly * n + rj] = v;
+  }
+  __syncthreads();
+
+  const int bflies = elems >> 1;
+  for (int s = 1; s <= log_n; s++) {
+    const int h = 1 << (s - 1);
+    const int tw_stride = n >> s;
+    for (int t = threadIdx.x; t < bflies; t += 256) {
+      int poly = t / (n >> 1), bt = t - poly * (n >> 1);
+      int pos = bt & (h - 1);
+      int i0 = poly * n + ((bt >> (s - 1)) << s) + pos;
+      int i1 = i0 + h;
+      Fe u = lds_fe(lo, hi, i0);
+      Fe v = lds_fe(lo, hi, i1);
+      if (s > 1) {
+        Fe w = ld_fe(a.tw + 2 * (pos * tw_stride));
+        v = mont_mul<F>(v, w);
+      }
+      sts_fe(lo, hi, i0, fe_add<F>(u, v));
+      sts_fe(lo, hi, i1, fe_sub<F>(u, v));
+    }
+    __syncthreads();
+  }
+
+  const int k_out = a.k_out;
+  for (int q = threadIdx.x; q < 2 * per_cta * k_out; q += 256) {
+    int e = q >> 1, half = q & 1;
+    int poly = e / k_out, i = e - poly * k_out;
+    if (first + poly < a.batch)
+      a.out[2ull * ((first + poly) * k_out + i) + half] = (half ? hi : lo)[poly * n + i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Large transforms (n > 1024): one global-memory pass per stage.
+// ---------------------------------------------------------------------------
+struct NttBigArgs {
+  uint4* work;        // [batch][n]
+  const uint4* in;    // [batch][d]
+  uint4* out;         // [batch][k_out]
+  const uint4* tw;    // [n/2]
+  unsigned long long batch;
+  int n, log_n, d, k_out, stage;
+};
+
+__global__ void __launch_bounds__(256) ntt_big_scatter_kernel(NttBigArgs a) {
+  unsigned long long g = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+  unsigned long long total = a.batch * (unsigned long long)a.n;
+  if (g >= total) return;
+  unsigned long long b = g >> a.log_n;
+  int j = (int)(g & (unsigned)(a.n - 1));
+  int d = a.d < a.n ? a.d : a.n;
+  uint4 z = make_uint4(0, 0, 0, 0), v0 = z, v1 = z;
+  if (j < d) {
+    v0 = a.in[2ull * (b * a.d + j)];
+    v1 = a.in[2ull * (b * a.d + j) + 1];
+  }
+  int rj = (int)(__brev((unsigned)j) >> (32 - a.log_n));
+  uint4* dst = a.work + 2ull * (b * a.n + rj);
+  dst[0] = v0;
+  dst[1] = v1;
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) ntt_big_stage_kernel(NttBigArgs a) {
+  unsigned long long g = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+  unsigned long long total = a.batch * (unsigned long long)(a.n >> 1);
+  if (g >= total) return;
+  const int s = a.stage, h = 1 << (s - 1);
+  unsigned long long b = g >> (a.log_n - 1);
+  int bt = (int)(g & (unsigned)((a.n >> 1) - 1));
+  int pos = bt & (h - 1);
+  unsigned long long i0 = b * a.n + (((unsigned)bt >> (s - 1)) << s) + pos;
+  unsigned long long i1 = i0 + h;
+  Fe u = ld_fe(a.work + 2 * i0);
+  Fe v = ld_fe(a.work + 2 * i1);
+  if (s > 1) {
+    Fe w = ld_fe(a.tw + 2ull * ((unsigned long long)pos * (a.n >> s)));
+    v = mont_mul<F>(v, w);
+  }
+  st_fe(a.work + 2 * i0, fe_add<F>(u, v));
+  st_fe(a.work + 2 * i1, fe_sub<F>(u, v));
+}
+
+__global__ void __launch_bounds__(256) ntt_big_gather_kernel(NttBigArgs a) {
+  unsigned long long g = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+  unsigned long long total = a.batch * (unsigned long long)a.k_out;
+  if (g >= total) return;
+  unsigned long long b = g / (unsigned)a.k_out;
+  int i = (int)(g - b * (unsigned)a.k_out);
+  const uint4* src = a.work + 2ull * (b * a.n + i);
+  uint4* dst = a.out + 2ull * g;
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
+}  // namespace hb

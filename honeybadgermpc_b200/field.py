@@ -1,0 +1,143 @@
+"""Prime field objects at the Python boundary of the reconstruction path.
+
+Mirrors the interface of the reference's ``honeybadgermpc/field.py`` (``GF``
+multiton :41-66, ``GFElement`` :68-290) as far as the path needs it: shares
+enter ``batch_reconstruct`` as ``GFElement`` and leave it as ``GFElement``
+(batch_reconstruction.py:126, :227); ``EvalPoint`` hands out ``GFElement``
+points.  Values cross into the CUDA library as ``.value`` ints.  No gmpy2: the
+primality check is a deterministic-base Miller-Rabin.
+"""
+
+from random import Random
+
+
+class FieldsNotIdentical(Exception):
+    pass
+
+
+_SMALL_PRIMES = (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47)
+
+
+def is_probable_prime(n):
+    if n < 2:
+        return False
+    for q in _SMALL_PRIMES:
+        if n % q == 0:
+            return n == q
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in _SMALL_PRIMES + (53, 59, 61, 67, 71):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+class GF:
+    """One object per modulus (field.py:41-58)."""
+
+    _cache = {}
+
+    def __new__(cls, modulus):
+        obj = cls._cache.get(modulus)
+        if obj is None:
+            if not is_probable_prime(int(modulus)):
+                raise ValueError(f"{modulus} is not a prime")
+            obj = super().__new__(cls)
+            obj.modulus = int(modulus)
+            cls._cache[modulus] = obj
+        return obj
+
+    def __call__(self, value):
+        return GFElement(value, self)
+
+    def __reduce__(self):
+        return (GF, (self.modulus,))
+
+    def random(self, seed=None):
+        # same draw as the reference (field.py:64-65) so get_omega(seed=0) agrees
+        return GFElement(Random(seed).randint(0, self.modulus - 1), self)
+
+
+class GFElement:
+    __slots__ = ("value", "field", "modulus")
+
+    def __init__(self, value, gf):
+        self.field = gf
+        self.modulus = gf.modulus
+        self.value = int(value) % gf.modulus
+
+    def _coerce(self, other):
+        if isinstance(other, GFElement):
+            if other.field is not self.field:
+                raise FieldsNotIdentical
+            return other.value
+        if isinstance(other, int):
+            return other
+        return None
+
+    def __int__(self):
+        return self.value
+
+    def __add__(self, other):
+        v = self._coerce(other)
+        return NotImplemented if v is None else GFElement(self.value + v, self.field)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        v = self._coerce(other)
+        return NotImplemented if v is None else GFElement(self.value - v, self.field)
+
+    def __rsub__(self, other):
+        return GFElement(other - self.value, self.field)
+
+    def __mul__(self, other):
+        v = self._coerce(other)
+        return NotImplemented if v is None else GFElement(self.value * v, self.field)
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return GFElement(-self.value, self.field)
+
+    def __pow__(self, e):
+        return GFElement(pow(self.value, e, self.modulus), self.field)
+
+    def inverse(self):
+        if self.value == 0:
+            raise ZeroDivisionError("inverse of 0")
+        return GFElement(pow(self.value, -1, self.modulus), self.field)
+
+    def __truediv__(self, other):
+        v = self._coerce(other)
+        if v is None:
+            return NotImplemented
+        return self * GFElement(v, self.field).inverse()
+
+    def __rtruediv__(self, other):
+        return GFElement(other, self.field) * self.inverse()
+
+    def __eq__(self, other):
+        if isinstance(other, GFElement):
+            return self.field is other.field and self.value == other.value
+        if isinstance(other, int):
+            return self.value == other % self.modulus
+        return NotImplemented
+
+    def __hash__(self):
+        return hash((self.value, self.modulus))
+
+    def __bool__(self):
+        return self.value != 0
+
+    def __repr__(self):
+        return "{%d}" % self.value

@@ -1,0 +1,118 @@
+/* hbmpc_b200 -- C-ABI of the B200-native batched share-reconstruction library.
+ *
+ * This is the drop-in boundary for HoneyBadgerMPC's native math layer.  Each
+ * entry point replaces one function the reference exports from its Cython/NTL
+ * extension `honeybadgermpc.ntl` (honeybadgermpc/ntl/hbmpc_ntl_helpers.pyx,
+ * algorithms in honeybadgermpc/ntl/rsdecode_impl.h); the reference-side binding
+ * a maintainer would add is the ctypes shim shown in INTEGRATION.md (ours is
+ * honeybadgermpc_b200/ntl/__init__.py).
+ *
+ * Conventions
+ *  - A field element is 4 x uint64_t little-endian limbs (32 bytes), the
+ *    canonical residue in [0, p).  Inputs MUST be canonical (the Python shim
+ *    reduces like the reference's to_ZZ_p does).  Outputs are canonical.
+ *  - Batch arrays are dense row-major: `rows[batch][width]` elements.
+ *  - `mem` says where the BATCH buffers (inputs and outputs) live:
+ *    HBG_MEM_HOST   -> the library stages them through device memory
+ *                      (cudaMemcpyAsync in, kernel, cudaMemcpyAsync out) and
+ *                      returns after the result is in the caller's buffer;
+ *    HBG_MEM_DEVICE -> device pointers on the context's device; the call only
+ *                      enqueues work on the context's stream (see
+ *                      hbg_ctx_set_stream / hbg_ctx_synchronize).
+ *    Point lists (xs, zs, omega) are always small HOST arrays.
+ *  - Every function returns an HBG_* code, never throws, never keeps a caller
+ *    pointer after returning.  The caller owns all buffers.
+ *  - All batch arithmetic runs in CUDA kernels (sm_100a).  There is no CPU
+ *    fallback: without a usable device hbg_ctx_create fails.
+ *    Host code only derives the O(n^2) per-point-set constants (Vandermonde
+ *    matrices and inverses, twiddles), which are cached in the context.
+ *  - A context is bound to one modulus and one device; it may be used from one
+ *    thread at a time.
+ */
+#ifndef HBMPC_B200_H
+#define HBMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBG_OK 0
+#define HBG_ERR_INVALID 1     /* bad argument (null pointer, size, non-canonical point, even modulus) */
+#define HBG_ERR_SINGULAR 2    /* repeated evaluation points: the reference raises InterpolationError
+                                 (hbmpc_ntl_helpers.pyx:168-169) */
+#define HBG_ERR_CUDA 3        /* a CUDA runtime call failed; see hbg_ctx_last_error */
+#define HBG_ERR_UNSUPPORTED 4 /* size outside what the kernels implement */
+#define HBG_ERR_NOMEM 5
+
+#define HBG_MEM_HOST 0
+#define HBG_MEM_DEVICE 1
+
+typedef struct hbg_ctx hbg_ctx;
+
+/* Library / build identification (also proves the CUDA library is the one loaded). */
+const char* hbg_version(void);
+
+/* Replaces NTL's per-call `ZZ_p::init(modulus)` (pyx:107,220,250,...): binds a
+ * modulus (odd, 3 <= p < 2^255) to a CUDA device and allocates the stream,
+ * scratch space and constant cache. */
+int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device);
+void hbg_ctx_destroy(hbg_ctx* ctx);
+const char* hbg_ctx_last_error(const hbg_ctx* ctx);
+/* Use the caller's CUDA stream (a cudaStream_t) for all work of this context;
+ * NULL restores the context's own stream. */
+int hbg_ctx_set_stream(hbg_ctx* ctx, void* cuda_stream);
+int hbg_ctx_synchronize(hbg_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx);
+/* Name of the dominant kernel of the last batch call (for bench.py / profiles). */
+const char* hbg_ctx_last_kernel(const hbg_ctx* ctx);
+/* The DFT of hbg_fft_batch_evaluate can run as radix-2 NTT butterflies or as
+ * Vandermonde row dot-products on the omega powers (the reference mixes both:
+ * a 16-point Vandermonde base case inside the recursion, rsdecode_impl.h:16,
+ * :133-136).  Results are bit-identical.  0 = pick the cheaper (default),
+ * 1 = dot products, 2 = butterflies. */
+int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path);
+
+/* vandermonde_batch_evaluate(x, polynomials, modulus), pyx:199-244 +
+ * set_vm_matrix rsdecode_impl.h:23-36:
+ *   out[b][i] = sum_{l<d} polys[b][l] * xs[i]^l,  b < batch, i < n. */
+int hbg_vandermonde_batch_evaluate(hbg_ctx* ctx, const uint64_t* xs, int n,
+                                   const uint64_t* polys, size_t batch, int d,
+                                   uint64_t* out, int mem);
+
+/* vandermonde_batch_interpolate(x, data_list, modulus), pyx:139-197 +
+ * vandermonde_inverse rsdecode_impl.h:97-122:
+ *   out[b] = V(xs)^-1 * ys[b]   (k coefficients, NOT stripped).
+ * HBG_ERR_SINGULAR if two xs coincide. */
+int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k,
+                                      const uint64_t* ys, size_t batch,
+                                      uint64_t* out, int mem);
+
+/* fft / partial_fft / fft_batch_evaluate(coeffs, omega, modulus, n, k),
+ * pyx:246-316 + fft/_fft rsdecode_impl.h:125-192:
+ *   out[b][i] = sum_{j<min(d,n)} polys[b][j] * omega^(i*j),  i < k_out <= n.
+ * n must be a power of two and omega a primitive n-th root of unity (the
+ * reference's Python callers guarantee this, polynomial.py:117-120; the
+ * library checks omega^n == 1 and omega^(n/2) == -1 and returns
+ * HBG_ERR_INVALID otherwise). */
+int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n,
+                           const uint64_t* polys, size_t batch, int d, int k_out,
+                           uint64_t* out, int mem);
+
+/* fft_interpolate / fft_batch_interpolate(zs, ys_list, omega, modulus, n),
+ * pyx:318-381 + fnt_decode_step1/2 rsdecode_impl.h:194-265:
+ *   out[b] = the k coefficients of the unique P, deg P < k, with
+ *   P(omega^zs[i]) = ys[b][i].   zs are k distinct exponents in [0, n).
+ * HBG_ERR_SINGULAR if a z repeats (the reference aborts in inv(0)). */
+int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n,
+                              const int32_t* zs, int k,
+                              const uint64_t* ys, size_t batch,
+                              uint64_t* out, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBMPC_B200_H */
