@@ -205,8 +205,9 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
   a.d = d;
   a.in_stride = in_stride;
   a.out_stride = out_stride;
-  unsigned long long total = (unsigned long long)batch * n_out;
-  unsigned long long blocks = (total + 255) / 256;
+  a.rows_per_cta = n_out <= 256 ? 256 / n_out : 1;
+  a.magic = (unsigned)(((1u << 20) + n_out - 1) / n_out);
+  unsigned long long blocks = (batch + a.rows_per_cta - 1) / a.rows_per_cta;
   if (blocks == 0) return HBG_OK;
   if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
   int rc = bind_field(ctx);
@@ -242,9 +243,12 @@ int check_omega(hbg_ctx* ctx, const uint64_t omega[4], int n, Fe& w_mont) {
   return HBG_OK;
 }
 
-int twiddles(hbg_ctx* ctx, const uint64_t omega[4], const Fe& w_mont, int n, const void** d_tw) {
+int twiddles(hbg_ctx* ctx, const uint64_t omega[4], int n, const void** d_tw) {
   std::string key = make_key("tw", omega, 32, nullptr, 0, n);
   return get_const(ctx, key, d_tw, [&](std::vector<uint32_t>& host) {
+    Fe w_mont;
+    int rc = check_omega(ctx, omega, n, w_mont);
+    if (rc) return rc;
     int half = n / 2 > 0 ? n / 2 : 1;
     host.resize((size_t)half * 8);
     Fe acc = ctx->field->one();
@@ -322,6 +326,21 @@ int launch_ntt(hbg_ctx* ctx, const void* d_tw, int n, const void* d_in, int d, v
   }
   ctx->last_kernel = "ntt_big_stage_kernel";
   return HBG_OK;
+}
+
+// V(x)^-1 for the k points produced by `points` (Montgomery form), cached by key.
+template <class Points>
+int interp_matrix(hbg_ctx* ctx, const std::string& key, int k, const void** d_m,
+                         Points points) {
+  return get_const(ctx, key, d_m, [&](std::vector<uint32_t>& host) {
+    std::vector<Fe> x_mont, inv;
+    int rc = points(x_mont);
+    if (rc) return rc;
+    if (!vandermonde_inverse(*ctx->field, x_mont, inv))
+      return fail(ctx, HBG_ERR_SINGULAR, "evaluation points are not pairwise distinct");
+    interleave(inv, k, k, host);
+    return HBG_OK;
+  });
 }
 
 }  // namespace
@@ -425,29 +444,15 @@ int hbg_vandermonde_batch_evaluate(hbg_ctx* ctx, const uint64_t* xs, int n, cons
   return unstage(ctx, out, batch * (size_t)n * 32, mem);
 }
 
-static int interp_matrix(hbg_ctx* ctx, const std::string& key, const std::vector<Fe>& x_mont,
-                         const void** d_m) {
-  int k = (int)x_mont.size();
-  return get_const(ctx, key, d_m, [&](std::vector<uint32_t>& host) {
-    std::vector<Fe> inv;
-    if (!vandermonde_inverse(*ctx->field, x_mont, inv))
-      return fail(ctx, HBG_ERR_SINGULAR, "evaluation points are not pairwise distinct");
-    interleave(inv, k, k, host);
-    return HBG_OK;
-  });
-}
-
 int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, const uint64_t* ys,
                                       size_t batch, uint64_t* out, int mem) {
   if (!ctx) return HBG_ERR_INVALID;
   if (k < 0 || (k && !xs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
   CU(cudaSetDevice(ctx->device));
-  std::vector<Fe> x;
-  int rc = load_points(ctx, xs, k, x);
-  if (rc) return rc;
   const void* d_m = nullptr;
   // the singularity check must run even for an empty batch (pyx:167-169)
-  rc = interp_matrix(ctx, make_key("vinv", xs, (size_t)k * 32, nullptr, 0, k), x, &d_m);
+  int rc = interp_matrix(ctx, make_key("vinv", xs, (size_t)k * 32, nullptr, 0, k), k, &d_m,
+                         [&](std::vector<Fe>& x) { return load_points(ctx, xs, k, x); });
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
   if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
@@ -465,10 +470,12 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   if (!omega || d < 0 || k_out < 0 || k_out > n)
     return fail(ctx, HBG_ERR_INVALID, "bad size or null omega");
   CU(cudaSetDevice(ctx->device));
-  Fe w;
-  int rc = check_omega(ctx, omega, n, w);
-  if (rc) return rc;
-  if (batch == 0 || k_out == 0) return HBG_OK;
+  if (n < 1 || (n & (n - 1)) != 0) return fail(ctx, HBG_ERR_INVALID, "fft size must be a power of two");
+  int rc;
+  if (batch == 0 || k_out == 0) {
+    Fe w;
+    return check_omega(ctx, omega, n, w);
+  }
   if (!out || (d && !polys)) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
   const int d_eff = d < n ? d : n;
   // cost in IMAD.WIDE per polynomial: dot products vs butterflies
@@ -483,8 +490,11 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   if (rc) return rc;
   if (use_matrix) {
     const void* d_m = nullptr;
-    rc = get_const(ctx, make_key("dft", omega, 32, nullptr, 0, k_out, d_eff), &d_m,
+    rc = get_const(ctx, make_key("dft", omega, 32, &n, sizeof n, k_out, d_eff), &d_m,
                    [&](std::vector<uint32_t>& host) {
+                     Fe w;
+                     int r = check_omega(ctx, omega, n, w);
+                     if (r) return r;
                      std::vector<Fe> m((size_t)k_out * (d_eff ? d_eff : 1), fe_zero());
                      Fe wi = ctx->field->one();  // omega^i
                      for (int i = 0; i < k_out; i++) {
@@ -502,7 +512,7 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
     rc = launch_matvec(ctx, d_m, k_out, d_eff, s.d_in, d, s.d_out, k_out, batch);
   } else {
     const void* d_tw = nullptr;
-    rc = twiddles(ctx, omega, w, n, &d_tw);
+    rc = twiddles(ctx, omega, n, &d_tw);
     if (rc) return rc;
     rc = launch_ntt(ctx, d_tw, n, s.d_in, d, s.d_out, k_out, batch);
   }
@@ -516,16 +526,20 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
   if (!omega || k < 0 || (k && !zs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
   if (k > 4096) return fail(ctx, HBG_ERR_UNSUPPORTED, "interpolation from more than 4096 points");
   CU(cudaSetDevice(ctx->device));
-  Fe w;
-  int rc = check_omega(ctx, omega, n, w);
-  if (rc) return rc;
-  std::vector<Fe> x(k);
-  for (int i = 0; i < k; i++) {
-    if (zs[i] < 0 || zs[i] >= n) return fail(ctx, HBG_ERR_INVALID, "z outside [0, n)");
-    x[i] = ctx->field->pow_u64(w, (uint64_t)zs[i]);
-  }
   const void* d_m = nullptr;
-  rc = interp_matrix(ctx, make_key("finv", omega, 32, zs, (size_t)k * 4, n, k), x, &d_m);
+  int rc = interp_matrix(ctx, make_key("finv", omega, 32, zs, (size_t)k * 4, n, k), k, &d_m,
+                         [&](std::vector<Fe>& x) {
+                           Fe w;
+                           int r = check_omega(ctx, omega, n, w);
+                           if (r) return r;
+                           x.resize(k);
+                           for (int i = 0; i < k; i++) {
+                             if (zs[i] < 0 || zs[i] >= n)
+                               return fail(ctx, HBG_ERR_INVALID, "z outside [0, n)");
+                             x[i] = ctx->field->pow_u64(w, (uint64_t)zs[i]);
+                           }
+                           return HBG_OK;
+                         });
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
   if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");

@@ -131,10 +131,13 @@ class HostField {
     return acc;
   }
   Fe pow_u64(Fe base, uint64_t e) const {
-    Fe ex = fe_zero();
-    ex.w[0] = (uint32_t)e;
-    ex.w[1] = (uint32_t)(e >> 32);
-    return pow(base, ex);
+    Fe acc = one_;
+    while (e) {
+      if (e & 1) acc = mul(acc, base);
+      base = mul(base, base);
+      e >>= 1;
+    }
+    return acc;
   }
   // Fermat inverse (p prime).  Returns zero for zero input; callers check.
   Fe inv(const Fe& a) const {

@@ -43,16 +43,12 @@ struct MatvecArgs {
   unsigned long long batch;
   int n_out, d;
   int in_stride, out_stride;
+  int rows_per_cta;          // max(1, 256 / n_out)
+  unsigned magic;            // ceil(2^20 / n_out): t / n_out == (t * magic) >> 20 for t < 256
 };
 
 template <class F>
-__global__ void __launch_bounds__(256) apply_matrix_kernel(MatvecArgs a) {
-  unsigned long long g = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
-  unsigned long long total = a.batch * (unsigned long long)a.n_out;
-  if (g >= total) return;
-  unsigned long long b = g / (unsigned)a.n_out;
-  int i = (int)(g - b * (unsigned)a.n_out);
-  const uint4* row = a.in + 2ull * b * (unsigned)a.in_stride;
+HB_D Fe row_dot(const MatvecArgs& a, const uint4* row, int i) {
   const uint32_t* mcol = a.mt + i;
   Acc acc;
   acc_zero(acc);
@@ -70,8 +66,25 @@ __global__ void __launch_bounds__(256) apply_matrix_kernel(MatvecArgs a) {
     }
   }
   if (pending) acc_fold<F>(acc);
-  Fe r = acc_redc<F>(acc);
-  st_fe(a.out + 2ull * (b * (unsigned)a.out_stride + i), r);
+  return acc_redc<F>(acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) apply_matrix_kernel(MatvecArgs a) {
+  if (a.n_out <= 256) {
+    int rl = (int)((threadIdx.x * a.magic) >> 20);
+    int i = (int)threadIdx.x - rl * a.n_out;
+    unsigned long long b = (unsigned long long)blockIdx.x * a.rows_per_cta + rl;
+    if (rl >= a.rows_per_cta || b >= a.batch) return;
+    Fe r = row_dot<F>(a, a.in + 2ull * b * (unsigned)a.in_stride, i);
+    st_fe(a.out + 2ull * (b * (unsigned)a.out_stride + i), r);
+  } else {
+    unsigned long long b = blockIdx.x;
+    for (int i = threadIdx.x; i < a.n_out; i += 256) {
+      Fe r = row_dot<F>(a, a.in + 2ull * b * (unsigned)a.in_stride, i);
+      st_fe(a.out + 2ull * (b * (unsigned)a.out_stride + i), r);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -117,7 +130,7 @@ __global__ void __launch_bounds__(256) ntt_smem_kernel(NttArgs a) {
   // load + bit-reverse scatter (one uint4 half per step: fully coalesced)
   for (int q = threadIdx.x; q < 2 * elems; q += 256) {
     int e = q >> 1, half = q & 1;
-    int poly = e / n, j = e - poly * n;
+    int poly = e >> log_n, j = e & (n - 1);
     uint4 v = make_uint4(0, 0, 0, 0);
     if (j < d && first + poly < a.batch) v = a.in[2ull * ((first + poly) * a.d + j) + half];
     int rj = (int)(__brev((unsigned)j) >> (32 - log_n));
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(256) ntt_smem_kernel(NttArgs a) {
     const int h = 1 << (s - 1);
     const int tw_stride = n >> s;
     for (int t = threadIdx.x; t < bflies; t += 256) {
-      int poly = t / (n >> 1), bt = t - poly * (n >> 1);
+      int poly = t >> (log_n - 1), bt = t & ((n >> 1) - 1);
       int pos = bt & (h - 1);
       int i0 = poly * n + ((bt >> (s - 1)) << s) + pos;
       int i1 = i0 + h;
@@ -147,11 +160,11 @@ __global__ void __launch_bounds__(256) ntt_smem_kernel(NttArgs a) {
   }
 
   const int k_out = a.k_out;
-  for (int q = threadIdx.x; q < 2 * per_cta * k_out; q += 256) {
+  for (int q = threadIdx.x; q < 2 * elems; q += 256) {
     int e = q >> 1, half = q & 1;
-    int poly = e / k_out, i = e - poly * k_out;
-    if (first + poly < a.batch)
-      a.out[2ull * ((first + poly) * k_out + i) + half] = (half ? hi : lo)[poly * n + i];
+    int poly = e >> log_n, i = e & (n - 1);
+    if (i < k_out && first + poly < a.batch)
+      a.out[2ull * ((first + poly) * k_out + i) + half] = (half ? hi : lo)[e];
   }
 }
 

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU needed) into a small CSV + markdown
+table for profiles/:   python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/NAME"""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
+    "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed.sum",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    cols = [(w, hdr.index(w)) for w in WANT if w in hdr]
+    kn = hdr.index("Kernel Name")
+    with open(out + ".csv", "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["kernel"] + [f"{c} [{units[i]}]" for c, i in cols])
+        for r in rows[2:]:
+            w.writerow([r[kn]] + [r[i] for _, i in cols])
+    with open(out + ".md", "w") as fh:
+        fh.write(f"ncu --set full summary of `{rep}` (per launch)\n\n")
+        for r in rows[2:]:
+            fh.write(f"### {r[kn]}\n\n| metric | value | unit |\n|---|---|---|\n")
+            for c, i in cols:
+                fh.write(f"| {c} | {r[i]} | {units[i]} |\n")
+            fh.write("\n")
+    print("wrote", out + ".csv", out + ".md")
+
+
+if __name__ == "__main__":
+    main()
