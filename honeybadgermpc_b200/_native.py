@@ -70,6 +70,16 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]),
+    "hbg_gao_decode_batch": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_int]),
+    "hbg_wb_decode_batch": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_int]),
 }
 
 
@@ -186,6 +196,18 @@ class Context:
         zs = np.ascontiguousarray(zs, dtype=np.int32)
         self._check(self.lib.hbg_fft_batch_interpolate(
             self.handle, _ptr(omega), n, _ptr(zs), len(zs), _ptr(ys), batch, _ptr(out), mem))
+
+
+    def gao_decode_batch(self, xs, k, ys, batch, coeffs, locator, loc_stride, loc_len, status,
+                         mem=MEM_HOST):
+        self._check(self.lib.hbg_gao_decode_batch(
+            self.handle, _ptr(xs), len(xs), k, _ptr(ys), batch, _ptr(coeffs), _ptr(locator),
+            loc_stride, _ptr(loc_len), _ptr(status), mem))
+
+    def wb_decode_batch(self, xs, k, e_max, ys, batch, coeffs, out_len, status, mem=MEM_HOST):
+        self._check(self.lib.hbg_wb_decode_batch(
+            self.handle, _ptr(xs), len(xs), k, e_max, _ptr(ys), batch, _ptr(coeffs),
+            _ptr(out_len), _ptr(status), mem))
 
 
 _contexts = {}

@@ -14,6 +14,7 @@
 #include "../../include/hbmpc_b200.h"
 #include "host_math.hpp"
 #include "kernels.cuh"
+#include "robust_kernels.cuh"
 
 using namespace hb;
 
@@ -45,7 +46,8 @@ struct hbg_ctx {
   std::string err;
   uint64_t launches = 0;
   const char* last_kernel = "";
-  DevBuf in, out, work;
+  DevBuf in, out, work, work2;
+  int sm_count = 148;
   std::unordered_map<std::string, DevConst> cache;
   size_t cache_bytes = 0;
 };
@@ -72,8 +74,8 @@ int fail(hbg_ctx* c, int code, const std::string& msg) {
   } while (0)
 
 // FieldAny kernels read the modulus from the __constant__ bank of this module.
-int bind_field(hbg_ctx* ctx) {
-  if (ctx->is_bls) return HBG_OK;  // FieldBLS: immediates
+int bind_field(hbg_ctx* ctx, bool needs_constants = false) {
+  if (ctx->is_bls && !needs_constants) return HBG_OK;  // FieldBLS: immediates
   std::lock_guard<std::mutex> lk(g_field_mutex);
   DeviceFieldState& st = g_dev_field[ctx->device];
   if (st.valid && memcmp(&st.fp, &ctx->fp, sizeof(FieldParams)) == 0) return HBG_OK;
@@ -330,19 +332,253 @@ int launch_ntt(hbg_ctx* ctx, const void* d_tw, int n, const void* d_in, int d, v
 
 // V(x)^-1 for the k points produced by `points` (Montgomery form), cached by key.
 template <class Points>
-int interp_matrix(hbg_ctx* ctx, const std::string& key, int k, const void** d_m,
-                         Points points) {
+int interp_matrix(hbg_ctx* ctx, const std::string& key, int k, const void** d_m, Points points,
+                  bool montgomery_out = false) {
   return get_const(ctx, key, d_m, [&](std::vector<uint32_t>& host) {
     std::vector<Fe> x_mont, inv;
     int rc = points(x_mont);
     if (rc) return rc;
     if (!vandermonde_inverse(*ctx->field, x_mont, inv))
       return fail(ctx, HBG_ERR_SINGULAR, "evaluation points are not pairwise distinct");
+    if (montgomery_out) {  // entries * R: the product with standard-form data is in Montgomery form
+      Fe r2;
+      memcpy(r2.w, ctx->fp.r2, 32);
+      for (Fe& v : inv) v = ctx->field->mul(v, r2);
+    }
     interleave(inv, k, k, host);
     return HBG_OK;
   });
 }
 
+
+// ---------------------------------------------------------------------------
+// robust decoders
+// ---------------------------------------------------------------------------
+const size_t kMaxSmem = 227 * 1024;
+
+template <class K>
+int allow_big_smem(hbg_ctx* ctx, K kernel) {
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  return HBG_OK;
+}
+
+size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+}  // namespace
+
+extern "C" {
+
+int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const uint64_t* ys,
+                         size_t batch, uint64_t* coeffs, uint64_t* locator, int loc_stride,
+                         int32_t* loc_len, int32_t* status, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (m < 1 || k < 1 || !xs) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  const int thr = (m + k) / 2;  // rsdecode_impl.h:338
+  if (loc_stride < m - thr + 1 || loc_stride < 1)
+    return fail(ctx, HBG_ERR_INVALID, "loc_stride must be at least m - (m+k)/2 + 1");
+  if (mem != HBG_MEM_HOST && mem != HBG_MEM_DEVICE) return fail(ctx, HBG_ERR_INVALID, "bad mem flag");
+  CU(cudaSetDevice(ctx->device));
+  // constants: V(x)^-1 scaled into "double Montgomery" form (so that the interpolants come
+  // out of apply_matrix in Montgomery form) and g0 = prod (X - x_i)
+  const void* d_m = nullptr;
+  int rc = interp_matrix(ctx, make_key("gaoinv", xs, (size_t)m * 32, nullptr, 0, m), m, &d_m,
+                         [&](std::vector<Fe>& x) { return load_points(ctx, xs, m, x); }, true);
+  if (rc) return rc;
+  const void* d_g0 = nullptr;
+  rc = get_const(ctx, make_key("gaog0", xs, (size_t)m * 32, nullptr, 0, m), &d_g0,
+                 [&](std::vector<uint32_t>& host) {
+                   std::vector<Fe> x;
+                   int r = load_points(ctx, xs, m, x);
+                   if (r) return r;
+                   std::vector<Fe> g0 = build_from_roots(*ctx->field, x);
+                   host.resize(g0.size() * 8);
+                   for (size_t i = 0; i < g0.size(); i++) memcpy(&host[i * 8], g0[i].w, 32);
+                   return HBG_OK;
+                 });
+  if (rc) return rc;
+  if (batch == 0) return HBG_OK;
+  if (!ys || !coeffs || !locator || !loc_len || !status)
+    return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  const size_t per_warp = (size_t)8 * (m + 1) * 16;
+  int warps = (int)(kMaxSmem / per_warp);
+  if (warps < 1) return fail(ctx, HBG_ERR_UNSUPPORTED, "received word too long for shared memory");
+  if (warps > 8) warps = 8;
+
+  const size_t ys_b = batch * (size_t)m * 32, co_b = batch * (size_t)k * 32;
+  const size_t lo_b = batch * (size_t)loc_stride * 32, i_b = align16(batch * 4);
+  const uint4* d_ys;
+  uint8_t* d_out = nullptr;
+  uint4 *d_co, *d_lo;
+  int *d_len, *d_st;
+  if (mem == HBG_MEM_HOST) {
+    rc = ensure(ctx, ctx->in, ys_b);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->out, co_b + lo_b + 2 * i_b);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->in.p, ys, ys_b, cudaMemcpyHostToDevice, ctx->stream));
+    d_ys = (const uint4*)ctx->in.p;
+    d_out = (uint8_t*)ctx->out.p;
+    d_co = (uint4*)d_out;
+    d_lo = (uint4*)(d_out + co_b);
+    d_len = (int*)(d_out + co_b + lo_b);
+    d_st = (int*)(d_out + co_b + lo_b + i_b);
+  } else {
+    d_ys = (const uint4*)ys;
+    d_co = (uint4*)coeffs;
+    d_lo = (uint4*)locator;
+    d_len = loc_len;
+    d_st = status;
+  }
+  rc = ensure(ctx, ctx->work, ys_b);
+  if (rc) return rc;
+  rc = launch_matvec(ctx, d_m, m, m, d_ys, m, ctx->work.p, m, batch);
+  if (rc) return rc;
+  rc = bind_field(ctx, true);
+  if (rc) return rc;
+  GaoArgs a;
+  a.g0 = (const uint4*)d_g0;
+  a.g1 = (const uint4*)ctx->work.p;
+  a.coeffs = d_co;
+  a.locator = d_lo;
+  a.loc_len = d_len;
+  a.status = d_st;
+  a.batch = batch;
+  a.m = m;
+  a.k = k;
+  a.thr = thr;
+  a.loc_stride = loc_stride;
+  a.warps_per_cta = warps;
+  size_t blocks = (batch + warps - 1) / warps;
+  size_t cap = (size_t)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  size_t smem = per_warp * warps;
+  CU(cudaMemsetAsync(d_lo, 0, lo_b, ctx->stream));
+  if (ctx->is_bls) {
+    rc = allow_big_smem(ctx, gao_kernel<FieldBLS>);
+    if (rc) return rc;
+    gao_kernel<FieldBLS><<<(unsigned)blocks, 32 * warps, smem, ctx->stream>>>(a);
+  } else {
+    rc = allow_big_smem(ctx, gao_kernel<FieldAny>);
+    if (rc) return rc;
+    gao_kernel<FieldAny><<<(unsigned)blocks, 32 * warps, smem, ctx->stream>>>(a);
+  }
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "gao_kernel";
+  if (mem == HBG_MEM_HOST) {
+    CU(cudaMemcpyAsync(coeffs, d_co, co_b, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(locator, d_lo, lo_b, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(loc_len, d_len, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(status, d_st, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return HBG_OK;
+}
+
+int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_max,
+                        const uint64_t* ys, size_t batch, uint64_t* coeffs, int32_t* out_len,
+                        int32_t* status, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (m < 1 || k < 1 || e_max < 1 || !xs) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  if (mem != HBG_MEM_HOST && mem != HBG_MEM_DEVICE) return fail(ctx, HBG_ERR_INVALID, "bad mem flag");
+  CU(cudaSetDevice(ctx->device));
+  const int pw_stride = e_max + k;
+  const void* d_pw = nullptr;
+  int rc = get_const(ctx, make_key("wbpw", xs, (size_t)m * 32, nullptr, 0, m, pw_stride), &d_pw,
+                     [&](std::vector<uint32_t>& host) {
+                       std::vector<Fe> x;
+                       int r = load_points(ctx, xs, m, x);
+                       if (r) return r;
+                       host.resize((size_t)m * pw_stride * 8);
+                       for (int i = 0; i < m; i++) {
+                         Fe acc = ctx->field->one();
+                         for (int j = 0; j < pw_stride; j++) {
+                           memcpy(&host[((size_t)i * pw_stride + j) * 8], acc.w, 32);
+                           acc = ctx->field->mul(acc, x[i]);
+                         }
+                       }
+                       return HBG_OK;
+                     });
+  if (rc) return rc;
+  if (batch == 0) return HBG_OK;
+  if (!ys || !coeffs || !out_len || !status) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  const int nrows = m + 1, max_cols = 2 * e_max + k + 2;
+  const size_t scratch = ((size_t)2 * nrows + 2 * max_cols + 2 * m) * 16 +
+                         (size_t)((3 * max_cols + 8 + nrows + 3) & ~3) * 4;
+  const size_t mat = (size_t)2 * nrows * max_cols * 16;
+  const bool in_smem = scratch + mat <= kMaxSmem;
+  if (scratch > kMaxSmem) return fail(ctx, HBG_ERR_UNSUPPORTED, "system too large");
+  size_t blocks = batch;
+  size_t cap = (size_t)ctx->sm_count * (in_smem ? (kMaxSmem / (scratch + mat) > 8 ? 8 : kMaxSmem / (scratch + mat)) : 4);
+  if (blocks > cap) blocks = cap;
+
+  const size_t ys_b = batch * (size_t)m * 32, co_b = batch * (size_t)k * 32, i_b = align16(batch * 4);
+  const uint4* d_ys;
+  uint4* d_co;
+  int *d_len, *d_st;
+  if (mem == HBG_MEM_HOST) {
+    rc = ensure(ctx, ctx->in, ys_b);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->out, co_b + 2 * i_b);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->in.p, ys, ys_b, cudaMemcpyHostToDevice, ctx->stream));
+    d_ys = (const uint4*)ctx->in.p;
+    uint8_t* o = (uint8_t*)ctx->out.p;
+    d_co = (uint4*)o;
+    d_len = (int*)(o + co_b);
+    d_st = (int*)(o + co_b + i_b);
+  } else {
+    d_ys = (const uint4*)ys;
+    d_co = (uint4*)coeffs;
+    d_len = out_len;
+    d_st = status;
+  }
+  WbArgs a;
+  a.pw = (const uint4*)d_pw;
+  a.ys = d_ys;
+  a.coeffs = d_co;
+  a.out_len = d_len;
+  a.status = d_st;
+  a.work = nullptr;
+  a.work_stride = mat / 16;
+  a.batch = batch;
+  a.m = m;
+  a.k = k;
+  a.e_max = e_max;
+  a.pw_stride = pw_stride;
+  a.in_smem = in_smem ? 1 : 0;
+  if (!in_smem) {
+    rc = ensure(ctx, ctx->work2, mat * blocks);
+    if (rc) return rc;
+    a.work = (uint4*)ctx->work2.p;
+  }
+  rc = bind_field(ctx, true);
+  if (rc) return rc;
+  size_t smem = scratch + (in_smem ? mat : 0);
+  if (ctx->is_bls) {
+    rc = allow_big_smem(ctx, wb_kernel<FieldBLS>);
+    if (rc) return rc;
+    wb_kernel<FieldBLS><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+  } else {
+    rc = allow_big_smem(ctx, wb_kernel<FieldAny>);
+    if (rc) return rc;
+    wb_kernel<FieldAny><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+  }
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "wb_kernel";
+  if (mem == HBG_MEM_HOST) {
+    CU(cudaMemcpyAsync(coeffs, d_co, co_b, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_len, d_len, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(status, d_st, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return HBG_OK;
+}
+
+}  // extern "C"
+
+namespace {
 }  // namespace
 
 extern "C" {
@@ -371,6 +607,7 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
     return HBG_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = ctx;
   return HBG_OK;
 }
@@ -383,6 +620,7 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->in.p) cudaFree(ctx->in.p);
   if (ctx->out.p) cudaFree(ctx->out.p);
   if (ctx->work.p) cudaFree(ctx->work.p);
+  if (ctx->work2.p) cudaFree(ctx->work2.p);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx->field;
   delete ctx;

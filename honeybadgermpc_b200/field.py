@@ -29,6 +29,8 @@ def is_probable_prime(n):
         d //= 2
         s += 1
     for a in _SMALL_PRIMES + (53, 59, 61, 67, 71):
+        if a % n == 0:
+            continue
         x = pow(a, d, n)
         if x in (1, n - 1):
             continue

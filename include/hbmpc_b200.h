@@ -112,6 +112,33 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n,
                               const uint64_t* ys, size_t batch,
                               uint64_t* out, int mem);
 
+/* gao_interpolate(x, y, k, modulus, ...), pyx:389-439 + gao_interpolate /
+ * gao_interpolate_fft / partial_gcd, rsdecode_impl.h:281-405 -- batched: every
+ * row of ys is one received word on the SAME m points xs (erasures already
+ * removed by the caller, as pyx:399-403 does).  Per row:
+ *   status 0: coeffs[b] = the k message coefficients (zero padded),
+ *             locator[b][0..loc_len[b]) = the UN-normalised error locator v
+ *             (the Bezout cofactor the reference returns; [1] when no error);
+ *   status 1: decoding failed (the reference returns (None, None)).
+ * loc_stride (elements per locator row) must be >= m - (m+k)/2 + 1. */
+int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k,
+                         const uint64_t* ys, size_t batch,
+                         uint64_t* coeffs, uint64_t* locator, int loc_stride,
+                         int32_t* loc_len, int32_t* status, int mem);
+
+/* Welch-Berlekamp decode (reed_solomon_wb.py:79-151: solve_system / rref /
+ * some_solution) -- batched: every row of ys is one received word on the same
+ * m points xs (erasures removed), e_max = (m - (k-1)) / 2 >= 1 as computed at
+ * reed_solomon_wb.py:134.  Per row:
+ *   status 0: coeffs[b][0..out_len[b]) = P = Q/E with trailing zeros stripped
+ *             (the rest of the row is zero);
+ *   status 1: ValueError("found no divisors!")  -> caller returns (None, None);
+ *   status 2: Exception("No solution")          -> propagates in the reference;
+ *   status 3: E came out as the zero polynomial (division by zero). */
+int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_max,
+                        const uint64_t* ys, size_t batch,
+                        uint64_t* coeffs, int32_t* out_len, int32_t* status, int mem);
+
 #ifdef __cplusplus
 }
 #endif

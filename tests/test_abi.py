@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: the CUDA library builds and loads,
+exports every symbol declared in include/hbmpc_b200.h (no compute calls -- there
+is no GPU here), the Python shim fails loudly without a device, and the product
+package never imports the oracle."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+from conftest import BLS12_381_R as P
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hbmpc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hbg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = graft.build_cuda()
+    lib = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 13
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in hbmpc_b200.h but not exported"
+    lib.hbg_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.hbg_version()
+
+
+def test_binding_covers_header():
+    from honeybadgermpc_b200 import _native
+
+    assert sorted(_native.SIGNATURES) == _declared_symbols()
+    _native.load_library()
+
+
+def test_sass_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "honeybadgermpc_b200", "libhbmpc_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from honeybadgermpc_b200 import ntl
+    from honeybadgermpc_b200._native import NativeLibraryError
+
+    for call in (lambda: ntl.vandermonde_batch_evaluate([1, 2], [[0, 1]], P),
+                 lambda: ntl.fft([0, 1], 5, 13, 4),
+                 lambda: ntl.gao_interpolate([1, 2, 3], [1, 2, 3], 1, P),
+                 lambda: ntl.lagrange_interpolate([1, 2], [1, 2], P)):
+        with pytest.raises(NativeLibraryError):
+            call()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "honeybadgermpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "cpu_ref" not in text and "hbmpc_oracle" not in text, f
+
+
+def test_host_marshalling_round_trip():
+    from honeybadgermpc_b200.ntl import pack_rows, unpack_rows
+
+    rows = [[0, 1, P - 1], [P, 2 * P + 5], []]
+    arr = pack_rows(rows, 3, P)
+    assert arr.shape == (3, 3, 4)
+    assert unpack_rows(arr) == [[0, 1, P - 1], [0, 5, 0], [0, 0, 0]]
+    with pytest.raises(OverflowError):
+        pack_rows([[-1]], 1, P)

@@ -1,0 +1,244 @@
+"""The codec objects, IncrementalDecoder and batch_reconstruct on the CUDA
+path: the reference's known answers (tests/test_reed_solomon.py,
+tests/test_batch_reconstruction.py, tests/test_offline_randousha.py algebra)
+and randomized parity against the oracle.  ``pytest -m gpu``."""
+
+import asyncio
+import random
+
+import pytest
+from conftest import BLS12_381_R as P
+from sim_net import SimNet, run
+
+from oracle import hbmpc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rs():
+    from honeybadgermpc_b200 import ntl, reed_solomon
+
+    ntl._ctx(P)
+    return reed_solomon
+
+
+def _point(n, omega, p=P):
+    from honeybadgermpc_b200.field import GF
+    from honeybadgermpc_b200.polynomial import EvalPoint
+
+    return EvalPoint(GF(p), n, omega)
+
+
+# --- tests/test_reed_solomon.py:19-165 ---------------------------------------
+
+
+def test_encoder_decoder_kats(rs):
+    pt = _point(4, False)
+    for enc in (rs.VandermondeEncoder(pt), rs.EncoderFactory.get(pt),
+                rs.EncoderFactory.get(pt, rs.Algorithm.VANDERMONDE)):
+        assert enc.encode([1, 2]) == [3, 5, 7, 9]
+        assert enc.encode([[1, 2], [2, 3]]) == [[3, 5, 7, 9], [5, 8, 11, 14]]
+    for dec in (rs.VandermondeDecoder(pt), rs.DecoderFactory.get(pt)):
+        assert dec.decode([1, 3], [5, 9]) == [1, 2]
+        assert dec.decode([1, 3], [[5, 9], [8, 14]]) == [[1, 2], [2, 3]]
+    pto = _point(4, True)
+    w = pto.omega.value
+    want = [(1 + 2 * pow(w, i, P)) % P for i in range(4)]
+    want2 = [(2 + 3 * pow(w, i, P)) % P for i in range(4)]
+    for enc in (rs.FFTEncoder(pto), rs.VandermondeEncoder(pto), rs.OptimalEncoder(pto),
+                rs.EncoderFactory.get(pto), rs.EncoderFactory.get(pto, rs.Algorithm.FFT)):
+        assert enc.encode([1, 2]) == want
+        assert enc.encode([[1, 2], [2, 3]]) == [want, want2]
+    for dec in (rs.FFTDecoder(pto), rs.VandermondeDecoder(pto), rs.OptimalDecoder(pto)):
+        assert dec.decode([1, 3], [want[1], want[3]]) == [1, 2]
+        assert dec.decode([1, 3], [[want[1], want[3]], [want2[1], want2[3]]]) == [[1, 2], [2, 3]]
+    with pytest.raises(ValueError):
+        rs.EncoderFactory.get(pt, "nope")
+    with pytest.raises(ValueError):
+        rs.DecoderFactory.get(pt, rs.Algorithm.GAO)
+    with pytest.raises(ValueError):
+        rs.RobustDecoderFactory.get(1, pt, rs.Algorithm.FFT)
+
+
+def test_selectors(rs, monkeypatch):
+    """tests/test_reed_solomon.py:186-277: which class the heuristics pick"""
+    from honeybadgermpc_b200 import ntl
+
+    monkeypatch.setattr("psutil.cpu_count", lambda logical=False: 4)
+    for n, cls in [(4, rs.VandermondeEncoder), (8, rs.FFTEncoder), (9, rs.VandermondeEncoder),
+                   (13, rs.FFTEncoder), (65, rs.VandermondeEncoder), (100, rs.FFTEncoder),
+                   (128, rs.FFTEncoder), (129, rs.FFTEncoder)]:
+        assert type(rs.EncoderSelector.select(_point(n, True), 1)) is cls, n
+    rs.DecoderSelector.set_optimal_thread_count(100)
+    assert ntl.AvailableNTLThreads() == 4
+    assert type(rs.DecoderSelector.select(_point(4, True), 1)) is rs.VandermondeDecoder
+    nt = ntl.AvailableNTLThreads()
+    assert type(rs.DecoderSelector.select(_point(16, True), int(0.5 * 16 * nt))) is rs.FFTDecoder
+    assert type(rs.DecoderSelector.select(_point(16, True), int(0.5 * 16 * nt) + 1)) is rs.VandermondeDecoder
+    rs.DecoderSelector.set_optimal_thread_count(1)
+    assert ntl.AvailableNTLThreads() == 1
+
+
+@pytest.mark.parametrize("n,t,omega", [(4, 1, False), (7, 2, True), (16, 5, False), (16, 5, True)])
+def test_codec_round_trip_vs_oracle(rs, n, t, omega):
+    rng = random.Random(n * 10 + t)
+    pt = _point(n, omega)
+    opt = orc.EvalPoint(P, n, omega)
+    xs = [opt(i) for i in range(n)]
+    enc, dec = rs.EncoderFactory.get(pt), rs.DecoderFactory.get(pt)
+    polys = [[rng.randrange(P) for _ in range(t + 1)] for _ in range(33)]
+    encoded = enc.encode(polys)
+    assert encoded == orc.vandermonde_batch_evaluate(xs, polys, P)
+    z = rng.sample(range(n), t + 1)
+    assert dec.decode(z, [[row[i] for i in z] for row in encoded]) == polys
+
+
+# --- IncrementalDecoder -------------------------------------------------------
+
+
+def _inc(rs, n, t, omega, batch, algo="gao"):
+    pt = _point(n, omega)
+    kind = rs.Algorithm.FFT if omega else rs.Algorithm.VANDERMONDE
+    return pt, rs.IncrementalDecoder(
+        rs.EncoderFactory.get(pt, kind), rs.DecoderFactory.get(pt, kind),
+        rs.RobustDecoderFactory.get(t, pt, algo), degree=t, batch_size=batch, max_errors=t)
+
+
+@pytest.mark.parametrize("omega", [False, True])
+@pytest.mark.parametrize("algo", ["gao", "welch-berlekamp"])
+def test_incremental_decoder(rs, omega, algo):
+    rng = random.Random(17)
+    n, t, batch = 7, 2, 9
+    opt = orc.EvalPoint(P, n, omega)
+    polys = [[rng.randrange(P) for _ in range(t + 1)] for _ in range(batch)]
+    cols = [[orc.poly_eval(c, opt(i), P) for c in polys] for i in range(n)]
+
+    # no faults: done after t+1+t columns, in any arrival order
+    pt, inc = _inc(rs, n, t, omega, batch, algo)
+    order = [4, 0, 6, 2, 5, 1, 3]
+    for count, i in enumerate(order, 1):
+        inc.add(i, cols[i])
+        assert inc.done() == (count >= 2 * t + 1)
+        if inc.done():
+            break
+    res, errs = inc.get_results()
+    assert res == polys and errs == set()
+    inc.add(3, cols[3])  # ignored once done
+
+    # duplicate columns are ignored, wrong length is rejected
+    pt, inc = _inc(rs, n, t, omega, batch, algo)
+    inc.add(0, cols[0])
+    inc.add(0, cols[1])
+    with pytest.raises(rs.DecodeValidationError):
+        inc.add(1, cols[1][:-1])
+    assert inc.get_results() == (None, None)
+
+    if algo == "gao":
+        # one Byzantine party inside the first t+1 columns, another one later
+        bad = {1: [(v + 1) % P for v in cols[1]], 5: [0] * batch}
+        pt, inc = _inc(rs, n, t, omega, batch, algo)
+        for i in [1, 0, 2, 3, 5, 4]:
+            inc.add(i, bad.get(i, cols[i]))
+            assert not inc.done()
+        inc.add(6, cols[6])
+        assert inc.done()
+        res, errs = inc.get_results()
+        assert res == polys and errs == {1, 5}
+    else:
+        # Welch-Berlekamp raises "No solution" when a word is beyond capacity (the
+        # reference does not catch it, reed_solomon.py:205-212), so stay within it
+        bad = {4: [0] * batch}
+        pt, inc = _inc(rs, n, t, omega, batch, algo)
+        for i in [0, 1, 2, 3, 4]:
+            inc.add(i, bad.get(i, cols[i]))
+            assert not inc.done()
+        inc.add(5, cols[5])
+        assert inc.done()
+        res, errs = inc.get_results()
+        assert res == polys and errs == {4}
+
+    # a party that lies in ONE row only is still found and evicted
+    sly = list(cols[2])
+    sly[4] = (sly[4] + 5) % P
+    pt, inc = _inc(rs, n, t, omega, batch, algo)
+    for i in [0, 1, 2, 3, 4, 5]:
+        inc.add(i, sly if i == 2 else cols[i])
+    assert inc.done()
+    res, errs = inc.get_results()
+    assert res == polys and errs == {2}
+
+
+# --- batch_reconstruct (tests/test_batch_reconstruction.py:12-170) -------------
+
+
+async def _reconstruct(n, t, shares, omega, skip=(), zero=(), delay=0.0, config=None):
+    from honeybadgermpc_b200.batch_reconstruction import batch_reconstruct
+    from honeybadgermpc_b200.field import GF
+
+    fp = GF(P)
+    net = SimNet(n, max_delay=delay, seed=5)
+    jobs = []
+    for i in range(n):
+        if i in skip:
+            continue
+        ss = [fp(0) for _ in shares[i]] if i in zero else [fp(v) for v in shares[i]]
+        jobs.append(batch_reconstruct(ss, P, t, n, i, net.sends[i], net.recvs[i],
+                                      use_omega_powers=omega, config=config))
+    return await asyncio.gather(*jobs)
+
+
+def test_batch_reconstruct_kats():
+    from honeybadgermpc_b200.field import GFElement
+
+    shares = [(3, 7, 4), (4, 10, 6), (5, 13, 8), (6, 16, 10)]  # x+2, 3x+4, 2x+2
+    for zero in ((), (1,)):
+        for r in run(_reconstruct(4, 1, shares, False, zero=zero, delay=0.01)):
+            assert all(type(e) is GFElement for e in r)
+            assert r == [2, 4, 2]
+    w = _point(4, True).omega.value
+    oshares = [((pow(w, i, P) + 2) % P, (3 * pow(w, i, P) + 4) % P) for i in range(4)]
+    for zero in ((), (1,)):
+        for r in run(_reconstruct(4, 1, oshares, True, zero=zero)):
+            assert r == [2, 4]
+
+
+@pytest.mark.parametrize("n,t,count,omega,algo", [(4, 1, 256, False, "gao"), (7, 2, 100, True, "gao"),
+                                                  (16, 5, 64, False, "welch-berlekamp"),
+                                                  (16, 5, 601, True, "gao")])
+def test_batch_reconstruct_random(n, t, count, omega, algo):
+    """BASELINE config 1 shape (n=4, t=1, 256 shares) and larger: every honest
+    party opens the secrets, also with t parties sending zeros"""
+    rng = random.Random(count)
+    opt = orc.EvalPoint(P, n, omega)
+    secrets = [rng.randrange(P) for _ in range(count)]
+    polys = [[s] + [rng.randrange(P) for _ in range(t)] for s in secrets]
+    shares = [[orc.poly_eval(c, opt(i), P) for c in polys] for i in range(n)]
+
+    class Cfg:
+        induce_faults = False
+        decoding_algorithm = algo
+
+    nbad = t if algo == "gao" else 1  # WB raises beyond capacity, see test_incremental_decoder
+    for zero in ((), tuple(rng.sample(range(n), nbad))):
+        results = run(_reconstruct(n, t, shares, omega, zero=zero, delay=0.002, config=Cfg))
+        for r in results:
+            assert [e.value for e in r] == secrets
+
+
+def test_randousha_refinement_algebra(rs):
+    """offline_randousha.py:72-78: the hyper-invertible step is
+    encoder.encode(transpose(received)) on the points 1..n (config 4 shape)"""
+    rng = random.Random(4)
+    n, t, rows = 16, 5, 50
+    pt = _point(n, False)
+    enc = rs.EncoderFactory.get(pt)
+    received = [[rng.randrange(P) for _ in range(n)] for _ in range(rows)]
+    out = enc.encode(received)
+    xs = list(range(1, n + 1))
+    assert out == orc.vandermonde_batch_evaluate(xs, received, P)
+    # degree check of the reference (offline_randousha.py:105-110): decode from all n points
+    dec = rs.DecoderFactory.get(pt)
+    polys = [[rng.randrange(P) for _ in range(t + 1)] + [0] * (n - t - 1) for _ in range(rows)]
+    shares = enc.encode(polys)
+    assert dec.decode(list(range(n)), shares) == polys

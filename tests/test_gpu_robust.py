@@ -1,0 +1,218 @@
+"""Parity of the CUDA Gao and Welch-Berlekamp decoders with the oracle and the
+reference's known answers (error positions, failure modes, p = 53 corner
+cases).  ``pytest -m gpu``."""
+
+import random
+
+import kats
+import numpy as np
+import pytest
+from conftest import BLS12_381_R as P
+
+from oracle import hbmpc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ntl():
+    from honeybadgermpc_b200 import ntl as m
+
+    m._ctx(P)
+    return m
+
+
+@pytest.fixture(scope="module")
+def rs():
+    from honeybadgermpc_b200 import reed_solomon
+
+    return reed_solomon
+
+
+def _point(p, n, omega):
+    from honeybadgermpc_b200.field import GF
+    from honeybadgermpc_b200.polynomial import EvalPoint
+
+    return EvalPoint(GF(p), n, omega)
+
+
+def test_gao_kats(ntl):
+    kats.check_gao(ntl)
+
+
+def _enc(coeffs, xs, p):
+    return [orc.poly_eval(coeffs, x, p) for x in xs]
+
+
+@pytest.mark.parametrize("p", [P, 53, 257])
+def test_gao_vs_oracle_random(ntl, p):
+    """random words incl. too many errors, erasures and degenerate inputs"""
+    rng = random.Random(p % 97)
+    for trial in range(60):
+        n = rng.choice([4, 7, 10, 16, 22]) if p > 30 else 10
+        n = min(n, p - 1)
+        k = rng.randint(1, max(1, n // 2))
+        xs = rng.sample(range(p), n) if p < 1000 else [rng.randrange(p) for _ in range(n)]
+        msg = [rng.randrange(p) for _ in range(k)]
+        if trial % 7 == 0:
+            msg = [0] * k
+        word = _enc(msg, xs, p)
+        nerr = rng.randint(0, n - k + 1)
+        for i in rng.sample(range(n), min(nerr, n)):
+            word[i] = rng.randrange(p)
+        for i in rng.sample(range(n), rng.randint(0, max(0, (n - k) // 2))):
+            word[i] = None
+        if sum(v is not None for v in word) == 0:
+            continue
+        want = orc.gao_interpolate(xs, word, k, p)
+        got = ntl.gao_interpolate(xs, word, k, p)
+        assert got == want, (trial, n, k, xs, word)
+
+
+def test_gao_batch_vs_oracle(ntl):
+    from honeybadgermpc_b200 import robust
+
+    rng = random.Random(3)
+    for n, k, batch in [(16, 6, 40), (64, 22, 24), (22, 8, 17)]:
+        pt = orc.EvalPoint(P, n, True)
+        xs = [pt(i) for i in range(n)]
+        rows, wants = [], []
+        for b in range(batch):
+            msg = [rng.randrange(P) for _ in range(k)]
+            word = _enc(msg, xs, P)
+            nerr = rng.choice([0, 0, 1, (n - k) // 2, (n - k) // 2, (n - k) // 2 + 1, n - k])
+            for i in rng.sample(range(n), nerr):
+                word[i] = (word[i] + 1 + rng.randrange(P - 1)) % P
+            rows.append(word)
+            wants.append(orc.gao_interpolate(xs, word, k, P))
+        coeffs, locator, loc_len, status = robust.gao_decode_batch_limbs(
+            ntl.pack_vec(xs, P), ntl.pack_rows(rows, n, P), k, P)
+        ci, li = ntl.unpack_rows(coeffs), ntl.unpack_rows(locator)
+        for b in range(batch):
+            if wants[b][0] is None:
+                assert status[b] == 1
+            else:
+                assert status[b] == 0
+                assert ci[b] == wants[b][0]
+                assert li[b][: loc_len[b]] == wants[b][1]
+
+
+def test_robust_decode_kats(rs):
+    # tests/test_reed_solomon.py:76-99,168-183: [3,5,0,9] -> ([1,2],[2]) for Gao and WB
+    for use_omega in (False, True):
+        pt = _point(P, 4, use_omega)
+        enc = [(2 * pt(i).value + 1) % P for i in range(4)]
+        enc[2] = 0
+        for algo in (rs.Algorithm.GAO, rs.Algorithm.WELCH_BERLEKAMP):
+            dec = rs.RobustDecoderFactory.get(1, pt, algo)
+            assert dec.robust_decode([0, 1, 2, 3], enc) == ([1, 2], [2])
+            assert dec.robust_decode([3, 1, 0, 2], [enc[3], enc[1], enc[0], enc[2]]) == ([1, 2], [2])
+
+
+def test_wb_golden(rs, golden):
+    from honeybadgermpc_b200 import robust
+
+    for case in golden["wb"]:
+        p, n, k = case["p"], case["n"], case["k"]
+        pt = _point(p, n, case["use_omega_powers"])
+        z = [i for i, v in enumerate(case["received"]) if v is not None]
+        row = [case["received"][i] for i in z]
+        xs = [pt(i).value for i in z]
+        if case["exception"] is not None:
+            name, msg = case["exception"].split(":", 1)
+            if msg == "found no divisors!":
+                assert robust.wb_decode_rows(xs, [row], n, n - len(z), k, p) == [None]
+            else:
+                with pytest.raises(Exception) as ei:
+                    robust.wb_decode_rows(xs, [row], n, n - len(z), k, p)
+                assert str(ei.value) == msg or type(ei.value).__name__ == name
+        else:
+            assert robust.wb_decode_rows(xs, [row], n, n - len(z), k, p) == [case["decoded"]], case["label"]
+            dec = rs.WelchBerlekampRobustDecoder(k - 1, pt)
+            assert dec.robust_decode(z, row) == (case["decoded"], case["error_positions"])
+
+
+def _wb_outcome(fn):
+    try:
+        return ("ok", fn())
+    except AssertionError:
+        raise
+    except Exception as e:  # noqa: BLE001
+        return ("raise", type(e).__name__, str(e))
+
+
+@pytest.mark.parametrize("p", [53, 257, P])
+def test_wb_vs_oracle_random(rs, p):
+    """WB incl. beyond-capacity words and tiny fields, where the reference's
+    syntactic pivot test and its failure modes matter"""
+    rng = random.Random(p % 89 + 1)
+    trials = 150 if p < 1000 else 40
+    for trial in range(trials):
+        n = rng.choice([4, 5, 7, 10, 13, 16])
+        t = rng.randint(0, (n - 1) // 3)
+        k = t + 1
+        use_omega = p == P and trial % 2 == 0
+        pt = _point(p, n, use_omega)
+        opt = orc.EvalPoint(p, n, use_omega)
+        msg = [rng.randrange(p) for _ in range(k)]
+        if trial % 9 == 0:
+            msg = [0] * k
+        xs_all = [opt(i) for i in range(n)]
+        word = _enc(msg, xs_all, p)
+        for i in rng.sample(range(n), rng.randint(0, min(n, t + 2))):
+            word[i] = rng.randrange(p)
+        c_max = n - 2 * t - 1
+        erase = rng.sample(range(n), rng.randint(0, c_max))
+        z = [i for i in range(n) if i not in erase]
+        rng.shuffle(z)
+        row = [word[i] for i in z]
+        want = _wb_outcome(lambda: orc.wb_robust_decode(z, row, n, k, p, opt))
+        dec = rs.WelchBerlekampRobustDecoder(t, pt)
+        got = _wb_outcome(lambda: dec.robust_decode(z, row))
+        if want[0] == "raise":
+            assert got[0] == "raise" and got[2] == want[2], (trial, want, got)
+        else:
+            assert got == want, (trial, n, k, z, row, want, got)
+
+
+def test_gao_equals_wb_when_decodable(rs):
+    rng = random.Random(8)
+    n, t = 16, 5
+    for use_omega in (False, True):
+        pt = _point(P, n, use_omega)
+        gao = rs.GaoRobustDecoder(t, pt)
+        wb = rs.WelchBerlekampRobustDecoder(t, pt)
+        rows, bads = [], []
+        for trial in range(12):
+            c = [rng.randrange(P) for _ in range(t + 1)]
+            enc = [orc.poly_eval(c, pt(i).value, P) for i in range(n)]
+            bad = sorted(rng.sample(range(n), trial % (t + 1)))
+            for i in bad:
+                enc[i] = (enc[i] + 1 + rng.randrange(P - 1)) % P
+            rows.append(enc)
+            bads.append((c, bad))
+        z = list(range(n))
+        assert gao.robust_decode_batch(z, rows) == bads
+        assert wb.robust_decode_batch(z, rows) == bads
+
+
+def test_wb_config3_shape(rs):
+    """BASELINE config 3 (n=64, t=21, 21 corrupted evaluations) on a few rows,
+    against the C-speed property: decode returns the message and the exact
+    error positions"""
+    rng = random.Random(0xB203)
+    n, t = 64, 21
+    pt = _point(P, n, False)
+    wb = rs.WelchBerlekampRobustDecoder(t, pt)
+    gao = rs.GaoRobustDecoder(t, pt)
+    rows, want = [], []
+    for _ in range(6):
+        c = [rng.randrange(P) for _ in range(t + 1)]
+        enc = [orc.poly_eval(c, i + 1, P) for i in range(n)]
+        bad = sorted(rng.sample(range(n), t))
+        for i in bad:
+            enc[i] = (enc[i] + 1 + rng.randrange(P - 1)) % P
+        rows.append(enc)
+        want.append((c, bad))
+    assert wb.robust_decode_batch(list(range(n)), rows) == want
+    assert gao.robust_decode_batch(list(range(n)), rows) == want
