@@ -175,7 +175,7 @@ class Context:
         return self.lib.hbg_ctx_last_kernel(self.handle).decode()
 
     def set_fft_path(self, path):
-        self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2}[path]))
+        self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2, "ntt-smem": 3}[path]))
 
     # -- batch operations (limb arrays or device pointers) ------------------
     def vandermonde_batch_evaluate(self, xs, polys, batch, d, out, mem=MEM_HOST):

@@ -394,85 +394,198 @@ HB_HD Fe mont_mul(const Fe& a, const Fe& b) {
 }
 
 
+// r = x + y + cin (8 words, cin in {0,1}), returns carry out
+HB_HD uint32_t add8c(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin) {
+#if defined(__CUDA_ARCH__)
+  uint32_t c;
+  asm("{\n\t.reg .u32 t;\n\t"
+      "add.cc.u32 t, %25, 0xffffffff;\n\t"  // carry flag := cin
+      "addc.cc.u32 %0, %9, %17;\n\t addc.cc.u32 %1, %10, %18;\n\t addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t addc.cc.u32 %4, %13, %21;\n\t addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t addc.cc.u32 %7, %16, %24;\n\t addc.u32 %8, 0, 0;\n\t}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(c)
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),
+        "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]),
+        "r"(cin));
+  return c;
+#else
+  uint64_t c = cin;
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)x[i] + y[i] + c;
+    r[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+// Row entry of the even/odd CIOS when the multiplier digit is zero:
+//   e[0] += o[1];  o = (o >> 64) + carry
+HB_HD void shift_row(uint32_t* e, uint32_t* o) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %8, %8, %1;\n\t"
+      "addc.cc.u32 %0, %2, 0;\n\t addc.cc.u32 %1, %3, 0;\n\t addc.cc.u32 %2, %4, 0;\n\t"
+      "addc.cc.u32 %3, %5, 0;\n\t addc.cc.u32 %4, %6, 0;\n\t addc.cc.u32 %5, %7, 0;\n\t"
+      "addc.u32 %6, 0, 0;\n\t mov.u32 %7, 0;"
+      : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]),
+        "+r"(o[7]), "+r"(e[0]));
+#else
+  uint64_t s = (uint64_t)e[0] + o[1];
+  e[0] = (uint32_t)s;
+  uint64_t c = s >> 32;
+  for (int j = 0; j < 6; j++) {
+    uint64_t v = (uint64_t)o[j + 2] + c;
+    o[j] = (uint32_t)v;
+    c = v >> 32;
+  }
+  o[6] = (uint32_t)c;
+  o[7] = 0;
+#endif
+}
+
+template <class F>
+HB_HD void redc_row(uint32_t* e, uint32_t* o, const uint32_t* p) {
+  if (F::kLowOnes) {
+    redc_row_low_ones(e, o, p[2], p[3], p[4], p[5], p[6], p[7]);
+  } else {
+    uint32_t m = e[0] * F::n0inv();
+    cmad4(o, p[1], p[3], p[5], p[7], m);
+    cmad4_top(e, o[7], p[0], p[2], p[4], p[6], m);
+  }
+}
+
+// a / R mod p for a < 2^256 (a need not be reduced): mont_mul(a, 1) without the
+// multiply rows.  Canonical output.
+template <class F>
+HB_HD Fe mont_redc_lo(const uint32_t* a) {
+  uint32_t x[8], y[8], p[8];
+  load_p<F>(p);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    x[2 * j] = a[2 * j];
+    x[2 * j + 1] = 0;
+    y[2 * j] = a[2 * j + 1];
+    y[2 * j + 1] = 0;
+  }
+  redc_row<F>(x, y, p);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    uint32_t* e = (i & 1) ? y : x;
+    uint32_t* o = (i & 1) ? x : y;
+    shift_row(e, o);
+    redc_row<F>(e, o, p);
+  }
+  Fe r;
+  uint32_t hi[8];
+#pragma unroll
+  for (int i = 0; i < 7; i++) hi[i] = y[i + 1];
+  hi[7] = 0;
+  add8(r.w, x, hi);
+  cond_sub_p<F>(r);
+  return r;
+}
+
 // ---------------------------------------------------------------------------
 // Lazy-reduction dot products.  A row dot product sum_j a_j*b_j is accumulated
 // as a 512-bit integer and Montgomery-reduced ONCE (instead of once per
-// product): 64 IMAD.WIDE per term + 64 (48 for BLS) per output.
+// product): 64 IMAD.WIDE per term + 48 (BLS) / 64 per output.
 //
-// Representation: value = w[0..16) + sum_i k[i] * 2^(32*(8+i)).  The k words
-// are deferred carries: every 4-product chain that ends at word t >= 8 drops
-// its carry-out into k[t-8] instead of rippling upwards, so each chain is one
-// short asm statement.  Only words >= 8 ever receive deferred carries, and the
-// Montgomery quotient digits depend on words < 8 only, so deferral is exact.
+// Representation: value = E + (O << 32) + deferred carries, with E = e[0..16)
+// (word w has weight 2^(32w)) and O = o[0..16) (word w has weight 2^(32(w+1))).
+// Products a_j*b_i land on E when i+j is even and on O when it is odd, so every
+// 32x32->64 multiply-add works on a 64-bit ALIGNED register pair and fuses into
+// one IMAD.WIDE.  A 4-product chain that starts at word s drops its carry-out
+// (destined for word s+8) into ke[s/2] / ko[s/2] instead of rippling upwards,
+// so each chain is one short asm statement; only words >= 8 receive deferred
+// carries, the low half is always exact.
 // ---------------------------------------------------------------------------
 struct Acc {
-  uint32_t w[16];
-  uint32_t k[8];
+  uint32_t e[16];
+  uint32_t o[16];
+  uint32_t ke[4], ko[4];
 };
 
 HB_HD void acc_zero(Acc& t) {
 #pragma unroll
-  for (int i = 0; i < 16; i++) t.w[i] = 0;
+  for (int i = 0; i < 16; i++) {
+    t.e[i] = 0;
+    t.o[i] = 0;
+  }
 #pragma unroll
-  for (int i = 0; i < 8; i++) t.k[i] = 0;
+  for (int i = 0; i < 4; i++) {
+    t.ke[i] = 0;
+    t.ko[i] = 0;
+  }
 }
 
 // t += a*b.  Caller keeps the true value below 2^512 (see acc_fold).
 HB_HD void acc_mac(Acc& t, const Fe& a, const Fe& b) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    cmad4_top(t.w + i, t.k[i], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
-    if (i < 7) {
-      cmad4_top(t.w + i + 1, t.k[i + 1], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+  for (int i = 0; i < 8; i += 2) {
+    // even digit b_i: a_even*b_i -> E[i..i+8), a_odd*b_i -> O[i..i+8)
+    cmad4_top(t.e + i, t.ke[i / 2], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
+    cmad4_top(t.o + i, t.ko[i / 2], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+    // odd digit b_{i+1}: a_odd*b -> E[i+2..i+10), a_even*b -> O[i..i+8)
+    if (i + 2 < 8) {
+      cmad4_top(t.e + i + 2, t.ke[i / 2 + 1], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i + 1]);
     } else {
-      cmad4(t.w + 8, a.w[1], a.w[3], a.w[5], a.w[7], b.w[7]);  // top chain: no carry out (< 2^512)
+      cmad4(t.e + 8, a.w[1], a.w[3], a.w[5], a.w[7], b.w[7]);  // top chain: value < 2^512
     }
+    cmad4_top(t.o + i, t.ko[i / 2], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i + 1]);
   }
 }
 
-// Resolve the deferred carries and bring the value below p*2^256 by one
-// conditional subtraction of p*2^256.  Precondition: value < 2*p*2^256 and
-// < 2^512.  With inputs a < p, b < p each product is < p^2 < 0.46*p*2^256, so
-// for the BLS field (p ~ 0.453*2^256) one fold per TWO macs keeps both bounds:
-// p*R + 2*p^2 < 2^512 * 0.87.  Generic fields fold after every mac
-// (p*R + p^2 < 2*p*R always; < 2^512 needs p < 2^255, else the host rejects).
+// Collapse E, O and the deferred carries into e[0..16) (o, ke, ko := 0) and bring
+// the value below p*2^256 by one conditional subtraction of p*2^256.
+// Precondition: value < 2*p*2^256 and < 2^512.  With inputs a < p, b < p each
+// product is < p^2 < 0.46*p*2^256, so for the BLS field (p ~ 0.453*2^256) one
+// fold per TWO macs keeps both bounds (p*R + 2*p^2 < 0.87 * 2^512).  Generic
+// fields fold after every mac (p*R + p^2 < 2*p*R; < 2^512 needs p < 2^255, which
+// hbg_ctx_create enforces).
 template <class F>
 HB_HD void acc_fold(Acc& t) {
-  uint32_t p[8], hi[8], d[8];
+  uint32_t p[8], lo[8], hi[8], d[8], sh[8], kk[8];
   load_p<F>(p);
-  add8(hi, t.w + 8, t.k);
+  // low half: e[0..8) + (o[0..7) << 32)
+  sh[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++) sh[i] = t.o[i - 1];
+  uint32_t c = add8(lo, t.e, sh);
+  // high half: e[8..16) + o[7..15) + carries
+#pragma unroll
+  for (int i = 0; i < 8; i++) sh[i] = t.o[7 + i];
+  add8c(hi, t.e + 8, sh, c);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    kk[2 * i] = t.ke[i];
+    kk[2 * i + 1] = t.ko[i];
+  }
+  add8(hi, hi, kk);
   uint32_t borrow = sub8(d, hi, p);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    t.w[8 + i] = borrow ? hi[i] : d[i];
-    t.k[i] = 0;
+    t.e[i] = lo[i];
+    t.e[8 + i] = borrow ? hi[i] : d[i];
+    t.o[i] = 0;
+    t.o[8 + i] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    t.ke[i] = 0;
+    t.ko[i] = 0;
   }
 }
 
-// Montgomery reduction of a folded accumulator (value < p*2^256): value/R mod p,
-// canonical.
+// Montgomery reduction of a folded accumulator (value = e[0..16) < p*2^256):
+// value/R mod p, canonical.   T/R = mont_redc_lo(T_lo) + T_hi  (mod p).
 template <class F>
 HB_HD Fe acc_redc(Acc& t) {
-  uint32_t p[8];
-  load_p<F>(p);
-  const uint32_t n0 = F::n0inv();
-  uint32_t k[9];
+  Fe lo = mont_redc_lo<F>(t.e);
+  Fe hi;
 #pragma unroll
-  for (int i = 0; i < 9; i++) k[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    uint32_t m = t.w[i] * n0;
-    cmad4_top(t.w + i, k[i], p[0], p[2], p[4], p[6], m);
-    if (i < 7) {
-      cmad4_top(t.w + i + 1, k[i + 1], p[1], p[3], p[5], p[7], m);
-    } else {
-      cmad4(t.w + 8, p[1], p[3], p[5], p[7], m);  // total < 2*p*2^256 < 2^512
-    }
-  }
-  Fe r;
-  add8(r.w, t.w + 8, k);
-  cond_sub_p<F>(r);
-  return r;
+  for (int i = 0; i < 8; i++) hi.w[i] = t.e[8 + i];
+  return fe_add<F>(lo, hi);
 }
 
 template <class F>

@@ -49,6 +49,7 @@ struct hbg_ctx {
   DevBuf in, out, work, work2;
   int sm_count = 148;
   std::unordered_map<std::string, DevConst> cache;
+  std::unordered_map<std::string, std::vector<uint32_t>> host_cache;  // small tables passed by value
   size_t cache_bytes = 0;
 };
 
@@ -120,6 +121,7 @@ int get_const(hbg_ctx* ctx, const std::string& key, const void** out, Build buil
     CU(cudaStreamSynchronize(ctx->stream));
     for (auto& kv : ctx->cache) cudaFree(kv.second.p);
     ctx->cache.clear();
+    ctx->host_cache.clear();
     ctx->cache_bytes = 0;
   }
   DevConst dc;
@@ -195,6 +197,14 @@ int unstage(hbg_ctx* ctx, void* out, size_t out_bytes, int mem) {
   return HBG_OK;
 }
 
+const size_t kMaxSmem = 226 * 1024;  // 227 KB opt-in limit minus room for static shared memory
+
+template <class K>
+int allow_big_smem(hbg_ctx* ctx, K kernel) {
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  return HBG_OK;
+}
+
 int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_in, int in_stride,
                   void* d_out, int out_stride, size_t batch) {
   MatvecArgs a;
@@ -214,6 +224,24 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
   if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
   int rc = bind_field(ctx);
   if (rc) return rc;
+  const size_t m_bytes = (size_t)n_out * d * 32;
+  const size_t tile_bytes = (size_t)a.rows_per_cta * d * 32;
+  if (n_out <= 256 && d >= 1 && in_stride == d && m_bytes <= 48 * 1024 && tile_bytes <= 64 * 1024) {
+    size_t smem = m_bytes + tile_bytes;
+    if (ctx->is_bls) {
+      rc = allow_big_smem(ctx, apply_matrix_smem_kernel<FieldBLS>);
+      if (rc) return rc;
+      apply_matrix_smem_kernel<FieldBLS><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+    } else {
+      rc = allow_big_smem(ctx, apply_matrix_smem_kernel<FieldAny>);
+      if (rc) return rc;
+      apply_matrix_smem_kernel<FieldAny><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+    }
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_kernel = "apply_matrix_smem_kernel";
+    return HBG_OK;
+  }
   if (ctx->is_bls)
     apply_matrix_kernel<FieldBLS><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
   else
@@ -245,12 +273,13 @@ int check_omega(hbg_ctx* ctx, const uint64_t omega[4], int n, Fe& w_mont) {
   return HBG_OK;
 }
 
-int twiddles(hbg_ctx* ctx, const uint64_t omega[4], int n, const void** d_tw) {
+int twiddles(hbg_ctx* ctx, const uint64_t omega[4], int n, const void** d_tw,
+             const std::vector<uint32_t>** h_tw) {
   std::string key = make_key("tw", omega, 32, nullptr, 0, n);
-  return get_const(ctx, key, d_tw, [&](std::vector<uint32_t>& host) {
+  int rc = get_const(ctx, key, d_tw, [&](std::vector<uint32_t>& host) {
     Fe w_mont;
-    int rc = check_omega(ctx, omega, n, w_mont);
-    if (rc) return rc;
+    int r = check_omega(ctx, omega, n, w_mont);
+    if (r) return r;
     int half = n / 2 > 0 ? n / 2 : 1;
     host.resize((size_t)half * 8);
     Fe acc = ctx->field->one();
@@ -258,14 +287,54 @@ int twiddles(hbg_ctx* ctx, const uint64_t omega[4], int n, const void** d_tw) {
       memcpy(&host[(size_t)i * 8], acc.w, 32);
       acc = ctx->field->mul(acc, w_mont);
     }
+    if (n <= 16) ctx->host_cache[key] = host;
     return HBG_OK;
   });
+  if (rc) return rc;
+  auto it = ctx->host_cache.find(key);
+  *h_tw = it == ctx->host_cache.end() ? nullptr : &it->second;
+  return HBG_OK;
 }
 
-int launch_ntt(hbg_ctx* ctx, const void* d_tw, int n, const void* d_in, int d, void* d_out,
-               int k_out, size_t batch) {
+template <class F, int D>
+void launch_ntt16_t(hbg_ctx* ctx, const Ntt16Args& a, unsigned blocks) {
+  ntt16_reg_kernel<F, D><<<blocks, 128, 0, ctx->stream>>>(a);
+}
+
+template <class F>
+void launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a, unsigned blocks) {
+  if (a.d <= 4) launch_ntt16_t<F, 4>(ctx, a, blocks);
+  else if (a.d <= 6) launch_ntt16_t<F, 6>(ctx, a, blocks);
+  else if (a.d <= 8) launch_ntt16_t<F, 8>(ctx, a, blocks);
+  else if (a.d <= 11) launch_ntt16_t<F, 11>(ctx, a, blocks);
+  else launch_ntt16_t<F, 16>(ctx, a, blocks);
+}
+
+int launch_ntt(hbg_ctx* ctx, const void* d_tw, const std::vector<uint32_t>* h_tw, int n,
+               const void* d_in, int d, void* d_out, int k_out, size_t batch) {
   int rc = bind_field(ctx);
   if (rc) return rc;
+  if (n == 16 && h_tw && ctx->fft_path != 3) {
+    Ntt16Args a;
+    a.in = (const uint4*)d_in;
+    a.out = (uint4*)d_out;
+    a.batch = batch;
+    a.d = d < 16 ? d : 16;
+    a.stride = d;
+    a.k_out = k_out;
+    memcpy(a.tw, h_tw->data(), sizeof(a.tw));
+    size_t blocks = (batch + 127) / 128;
+    if (blocks == 0) return HBG_OK;
+    if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
+    if (ctx->is_bls)
+      launch_ntt16_f<FieldBLS>(ctx, a, (unsigned)blocks);
+    else
+      launch_ntt16_f<FieldAny>(ctx, a, (unsigned)blocks);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_kernel = "ntt16_reg_kernel";
+    return HBG_OK;
+  }
   int log_n = ilog2(n);
   if (n <= 1024) {
     NttArgs a;
@@ -354,14 +423,6 @@ int interp_matrix(hbg_ctx* ctx, const std::string& key, int k, const void** d_m,
 // ---------------------------------------------------------------------------
 // robust decoders
 // ---------------------------------------------------------------------------
-const size_t kMaxSmem = 227 * 1024;
-
-template <class K>
-int allow_big_smem(hbg_ctx* ctx, K kernel) {
-  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  return HBG_OK;
-}
-
 size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 }  // namespace
@@ -644,7 +705,7 @@ uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches :
 const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 2) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 3) return HBG_ERR_INVALID;
   ctx->fft_path = path;
   return HBG_OK;
 }
@@ -721,7 +782,7 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   double cost_ntt = (double)(n / 2) * (ilog2(n) > 1 ? ilog2(n) - 1 : 0) * 120 + 1;
   bool use_matrix = n < 2 || cost_mat <= cost_ntt;
   if (ctx->fft_path == 1 && (size_t)k_out * d_eff <= (1u << 22)) use_matrix = true;
-  if (ctx->fft_path == 2 && n >= 2) use_matrix = false;
+  if (ctx->fft_path >= 2 && n >= 2) use_matrix = false;
   if ((size_t)k_out * d_eff > (1u << 22)) use_matrix = false;
   Staged s;
   rc = stage(ctx, polys, batch * (size_t)d * 32, out, batch * (size_t)k_out * 32, mem, s);
@@ -750,9 +811,10 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
     rc = launch_matvec(ctx, d_m, k_out, d_eff, s.d_in, d, s.d_out, k_out, batch);
   } else {
     const void* d_tw = nullptr;
-    rc = twiddles(ctx, omega, n, &d_tw);
+    const std::vector<uint32_t>* h_tw = nullptr;
+    rc = twiddles(ctx, omega, n, &d_tw, &h_tw);
     if (rc) return rc;
-    rc = launch_ntt(ctx, d_tw, n, s.d_in, d, s.d_out, k_out, batch);
+    rc = launch_ntt(ctx, d_tw, h_tw, n, s.d_in, d, s.d_out, k_out, batch);
   }
   if (rc) return rc;
   return unstage(ctx, out, batch * (size_t)k_out * 32, mem);

@@ -88,6 +88,156 @@ __global__ void __launch_bounds__(256) apply_matrix_kernel(MatvecArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// apply_matrix, shared-memory variant (the hot interpolate / small-matrix path):
+// the matrix (<= 48 KB) and the CTA's tile of input rows live in shared memory.
+// The input tile -- rows_per_cta consecutive rows = one contiguous byte range of
+// the batch array -- is fetched by ONE TMA bulk copy (cp.async.bulk, completion
+// on an mbarrier) issued by thread 0 while all threads stage the matrix.
+// ---------------------------------------------------------------------------
+HB_D void mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+HB_D void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+      "l"(gmem_src), "r"(bytes), "r"(b)
+      : "memory");
+}
+
+HB_D void mbar_wait(uint64_t* bar, unsigned phase) {
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(b),
+      "r"(phase)
+      : "memory");
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) apply_matrix_smem_kernel(MatvecArgs a) {
+  extern __shared__ uint4 smem[];
+  __shared__ alignas(8) uint64_t bar;
+  const int n_out = a.n_out, d = a.d;
+  uint4* xt = smem;                                         // [rows_per_cta][d] elements
+  uint32_t* sm = (uint32_t*)(smem + 2 * a.rows_per_cta * d);  // [d][8][n_out] words
+  const unsigned long long row0 = (unsigned long long)blockIdx.x * a.rows_per_cta;
+  unsigned long long rows_here = a.batch - row0;
+  if (rows_here > (unsigned long long)a.rows_per_cta) rows_here = a.rows_per_cta;
+  const unsigned tile_bytes = (unsigned)rows_here * d * 32u;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tma_load_1d(xt, a.in + 2ull * row0 * d, tile_bytes, &bar);
+  for (int q = threadIdx.x; q < d * 8 * n_out; q += 256) sm[q] = a.mt[q];
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  int rl = (int)((threadIdx.x * a.magic) >> 20);
+  int i = (int)threadIdx.x - rl * n_out;
+  if (rl >= (int)rows_here) return;
+  const uint4* row = xt + 2 * rl * d;
+  const uint32_t* mcol = sm + i;
+  Acc acc;
+  acc_zero(acc);
+  int pending = 0;
+#pragma unroll 2
+  for (int j = 0; j < d; j++) {
+    Fe x = ld_fe(row + 2 * j);
+    Fe m;
+#pragma unroll
+    for (int w = 0; w < 8; w++) m.w[w] = mcol[(j * 8 + w) * n_out];
+    acc_mac(acc, x, m);
+    if (++pending == F::kFold) {
+      acc_fold<F>(acc);
+      pending = 0;
+    }
+  }
+  if (pending) acc_fold<F>(acc);
+  Fe r = acc_redc<F>(acc);
+  st_fe(a.out + 2ull * ((row0 + rl) * (unsigned)a.out_stride + i), r);
+}
+
+// ---------------------------------------------------------------------------
+// 16-point NTT in registers, one polynomial per thread (the n = 16 encode of
+// the headline config; fft_batch_evaluate with n == 16).  Decimation in
+// frequency, fully unrolled; D = number of input coefficients is a template
+// parameter so structurally-zero operands are dropped at compile time
+// (d = 6: 15 modular multiplications instead of 32).  The 8 twiddles come from
+// the kernel-parameter constant bank.  Output i of the transform sits in slot
+// bitrev4(i).
+// ---------------------------------------------------------------------------
+struct Ntt16Args {
+  const uint4* in;    // [batch][d]
+  uint4* out;         // [batch][k_out]
+  unsigned long long batch;
+  int d, k_out, stride;  // d <= 16 coefficients used, rows are `stride` elements apart
+  uint32_t tw[8][8];      // omega^i, i < 8, Montgomery form
+};
+
+// After s DIF stages slot idx is a combination of the inputs j = idx (mod 16 >> s);
+// with only the first D inputs non-zero it can be non-zero iff (idx mod (16 >> s)) < D.
+#define HB_NTT16_NZ(s, idx, D) ((((idx) & ((16 >> (s)) - 1))) < (D))
+
+template <class F, int D>
+__global__ void __launch_bounds__(128) ntt16_reg_kernel(Ntt16Args a) {
+  unsigned long long b = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+  if (b >= a.batch) return;
+  Fe v[16];
+  const uint4* src = a.in + 2ull * b * a.stride;  // a.d <= D coefficients per row
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    if (j < D) v[j] = j < a.d ? ld_fe(src + 2 * j) : fe_zero();
+  }
+#pragma unroll
+  for (int s = 1; s <= 4; s++) {
+    const int h = 16 >> s;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int pos = t & (h - 1);
+      const int i0 = ((t & ~(h - 1)) << 1) | pos;
+      const int i1 = i0 + h;
+      const bool nz0 = HB_NTT16_NZ(s - 1, i0, D), nz1 = HB_NTT16_NZ(s - 1, i1, D);
+      if (!nz0 && !nz1) continue;
+      const int tw_idx = pos << (s - 1);  // omega^(pos * 2^(s-1))
+      Fe lo, hi;
+      if (!nz1) {
+        lo = v[i0];
+        hi = v[i0];
+      } else if (!nz0) {
+        lo = v[i1];
+        hi = fe_neg<F>(v[i1]);
+      } else {
+        lo = fe_add<F>(v[i0], v[i1]);
+        hi = fe_sub<F>(v[i0], v[i1]);
+      }
+      if (tw_idx != 0) {
+        Fe w;
+#pragma unroll
+        for (int q = 0; q < 8; q++) w.w[q] = a.tw[tw_idx][q];
+        hi = mont_mul<F>(hi, w);
+      }
+      v[i0] = lo;
+      v[i1] = hi;
+    }
+  }
+  uint4* dst = a.out + 2ull * b * a.k_out;
+#pragma unroll
+  for (int idx = 0; idx < 16; idx++) {
+    const int i = ((idx & 1) << 3) | ((idx & 2) << 1) | ((idx & 4) >> 1) | ((idx & 8) >> 3);
+    if (i < a.k_out) st_fe(dst + 2 * i, v[idx]);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Radix-2 NTT in shared memory (fft / partial_fft / fft_batch_evaluate,
 // rsdecode_impl.h:125-192).  n <= 1024.  A CTA of 256 threads transforms
 // max(1, 512/n) polynomials at a time; element planes are split in two uint4

@@ -73,7 +73,8 @@ const char* hbg_ctx_last_kernel(const hbg_ctx* ctx);
  * Vandermonde row dot-products on the omega powers (the reference mixes both:
  * a 16-point Vandermonde base case inside the recursion, rsdecode_impl.h:16,
  * :133-136).  Results are bit-identical.  0 = pick the cheaper (default),
- * 1 = dot products, 2 = butterflies. */
+ * 1 = dot products, 2 = butterflies, 3 = butterflies through the generic
+ * shared-memory kernel even where a register-resident kernel exists (n = 16). */
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path);
 
 /* vandermonde_batch_evaluate(x, polynomials, modulus), pyx:199-244 +

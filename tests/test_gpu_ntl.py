@@ -65,7 +65,7 @@ def test_errors(ntl):
 
 
 def test_golden(ntl, golden):
-    for path in ("auto", "matrix", "ntt"):
+    for path in ("auto", "matrix", "ntt", "ntt-smem"):
         ntl._ctx(P).set_fft_path(path)
         kats.check_golden(ntl, golden)
     ntl._ctx(P).set_fft_path("auto")
@@ -108,6 +108,8 @@ def test_worst_case_values(ntl):
 
 
 @pytest.mark.parametrize("r,d,k,batch", [(1, 2, 2, 3), (2, 3, 4, 70), (4, 6, 16, 300), (4, 16, 11, 65),
+                                         (4, 1, 16, 9), (4, 4, 16, 130), (4, 5, 7, 129), (4, 8, 16, 31),
+                                         (4, 9, 16, 33), (4, 11, 1, 5), (4, 12, 16, 200), (4, 20, 16, 77),
                                          (5, 20, 25, 64), (7, 43, 128, 21), (8, 100, 256, 5),
                                          (10, 700, 1024, 3), (11, 1500, 2048, 2), (12, 4096, 100, 1)])
 def test_fft_vs_oracle(ntl, r, d, k, batch):
@@ -116,7 +118,7 @@ def test_fft_vs_oracle(ntl, r, d, k, batch):
     omega = ROOTS_OF_UNITY[r] if r < len(ROOTS_OF_UNITY) else pow(7, (P - 1) // n, P)
     polys = [[rng.randrange(P) for _ in range(d)] for _ in range(batch)]
     want = orc.fft_batch_evaluate(polys, omega, P, n, k)
-    for path in ("matrix", "ntt"):
+    for path in ("matrix", "ntt", "ntt-smem"):
         if path == "matrix" and k * min(d, n) > 2 ** 18:
             continue
         ntl._ctx(P).set_fft_path(path)
