@@ -54,6 +54,7 @@ SIGNATURES = {
     "hbg_ctx_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "hbg_ctx_last_kernel": (ctypes.c_char_p, [ctypes.c_void_p]),
     "hbg_ctx_set_fft_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "hbg_ctx_set_matvec_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_vandermonde_batch_evaluate": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
@@ -176,6 +177,10 @@ class Context:
 
     def set_fft_path(self, path):
         self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2, "ntt-smem": 3}[path]))
+
+    def set_matvec_path(self, path):
+        self._check(self.lib.hbg_ctx_set_matvec_path(
+            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3}[path]))
 
     # -- batch operations (limb arrays or device pointers) ------------------
     def vandermonde_batch_evaluate(self, xs, polys, batch, d, out, mem=MEM_HOST):

@@ -4,6 +4,7 @@
 // kernels exclusively.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -42,7 +43,8 @@ struct hbg_ctx {
   FieldParams fp;
   HostField* field = nullptr;
   bool is_bls = false;
-  int fft_path = 0;  // 0 auto, 1 matrix, 2 ntt
+  int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel
+  int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel
   std::string err;
   uint64_t launches = 0;
   const char* last_kernel = "";
@@ -226,7 +228,8 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
   if (rc) return rc;
   const size_t m_bytes = (size_t)n_out * d * 32;
   const size_t tile_bytes = (size_t)a.rows_per_cta * d * 32;
-  if (n_out <= 256 && d >= 1 && in_stride == d && m_bytes <= 48 * 1024 && tile_bytes <= 64 * 1024) {
+  if (ctx->matvec_path != 1 && n_out <= 256 && d >= 1 && in_stride == d && m_bytes <= 48 * 1024 &&
+      tile_bytes <= 64 * 1024) {
     size_t smem = m_bytes + tile_bytes;
     if (ctx->is_bls) {
       rc = allow_big_smem(ctx, apply_matrix_smem_kernel<FieldBLS>);
@@ -297,17 +300,75 @@ int twiddles(hbg_ctx* ctx, const uint64_t omega[4], int n, const void** d_tw,
 }
 
 template <class F, int D>
-void launch_ntt16_t(hbg_ctx* ctx, const Ntt16Args& a, unsigned blocks) {
-  ntt16_reg_kernel<F, D><<<blocks, 128, 0, ctx->stream>>>(a);
+int launch_ntt16_t(hbg_ctx* ctx, const Ntt16Args& a) {
+  constexpr int POLYS = 64;  // per CTA of 128 threads
+  const size_t in_tile = (size_t)POLYS * a.d * 32, out_tile = (size_t)POLYS * ((2 * a.k_out) | 1) * 16;
+  const size_t smem = in_tile > out_tile ? in_tile : out_tile;
+  int rc = allow_big_smem(ctx, ntt16_split_kernel<F, D, POLYS>);
+  if (rc) return rc;
+  ntt16_split_kernel<F, D, POLYS><<<(unsigned)((a.batch + POLYS - 1) / POLYS), 2 * POLYS, smem, ctx->stream>>>(a);
+  return HBG_OK;
 }
 
 template <class F>
-void launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a, unsigned blocks) {
-  if (a.d <= 4) launch_ntt16_t<F, 4>(ctx, a, blocks);
-  else if (a.d <= 6) launch_ntt16_t<F, 6>(ctx, a, blocks);
-  else if (a.d <= 8) launch_ntt16_t<F, 8>(ctx, a, blocks);
-  else if (a.d <= 11) launch_ntt16_t<F, 11>(ctx, a, blocks);
-  else launch_ntt16_t<F, 16>(ctx, a, blocks);
+int launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a) {
+  if (a.d <= 4) return launch_ntt16_t<F, 4>(ctx, a);
+  if (a.d <= 6) return launch_ntt16_t<F, 6>(ctx, a);
+  if (a.d <= 8) return launch_ntt16_t<F, 8>(ctx, a);
+  if (a.d <= 11) return launch_ntt16_t<F, 11>(ctx, a);
+  return launch_ntt16_t<F, 16>(ctx, a);
+}
+
+// k x k interpolation with the matrix in the kernel-parameter constant bank
+template <class F, int K>
+int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const void* d_in, void* d_out,
+                          size_t batch) {
+  constexpr int T = 128;
+  SmallInterpArgs<K> a;
+  a.in = (const uint4*)d_in;
+  a.out = (uint4*)d_out;
+  a.batch = batch;
+  memcpy(a.m, m.data(), sizeof(a.m));
+  const size_t in_tile = (size_t)T * K * 32, out_tile = (size_t)T * ((2 * K) | 1) * 16;
+  const size_t smem = in_tile > out_tile ? in_tile : out_tile;
+  interp_small_kernel<F, K, T><<<(unsigned)((batch + T - 1) / T), T, smem, ctx->stream>>>(a);
+  return HBG_OK;
+}
+
+template <class F>
+int launch_interp_small_f(hbg_ctx* ctx, int k, const std::vector<uint32_t>& m, const void* d_in,
+                          void* d_out, size_t batch) {
+  switch (k) {
+    case 1: return launch_interp_small_t<F, 1>(ctx, m, d_in, d_out, batch);
+    case 2: return launch_interp_small_t<F, 2>(ctx, m, d_in, d_out, batch);
+    case 3: return launch_interp_small_t<F, 3>(ctx, m, d_in, d_out, batch);
+    case 4: return launch_interp_small_t<F, 4>(ctx, m, d_in, d_out, batch);
+    case 5: return launch_interp_small_t<F, 5>(ctx, m, d_in, d_out, batch);
+    case 6: return launch_interp_small_t<F, 6>(ctx, m, d_in, d_out, batch);
+    case 7: return launch_interp_small_t<F, 7>(ctx, m, d_in, d_out, batch);
+    case 8: return launch_interp_small_t<F, 8>(ctx, m, d_in, d_out, batch);
+  }
+  return HBG_ERR_UNSUPPORTED;
+}
+
+// out[b] = M * in[b] for a cached k x k interpolation matrix: the register/constant-bank
+// kernel for k <= 8, the generic dot-product kernels otherwise.
+int launch_interp(hbg_ctx* ctx, const std::string& key, const void* d_m, int k, const void* d_in,
+                  void* d_out, size_t batch) {
+  auto it = ctx->host_cache.find(key);
+  bool small = k <= 8 && it != ctx->host_cache.end() && (ctx->matvec_path == 0 || ctx->matvec_path == 3);
+  if (!small) return launch_matvec(ctx, d_m, k, k, d_in, k, d_out, k, batch);
+  if (batch == 0) return HBG_OK;
+  if ((batch + 127) / 128 > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large");
+  int rc = bind_field(ctx);
+  if (rc) return rc;
+  rc = ctx->is_bls ? launch_interp_small_f<FieldBLS>(ctx, k, it->second, d_in, d_out, batch)
+                   : launch_interp_small_f<FieldAny>(ctx, k, it->second, d_in, d_out, batch);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "interp_small_kernel";
+  return HBG_OK;
 }
 
 int launch_ntt(hbg_ctx* ctx, const void* d_tw, const std::vector<uint32_t>* h_tw, int n,
@@ -323,16 +384,14 @@ int launch_ntt(hbg_ctx* ctx, const void* d_tw, const std::vector<uint32_t>* h_tw
     a.stride = d;
     a.k_out = k_out;
     memcpy(a.tw, h_tw->data(), sizeof(a.tw));
-    size_t blocks = (batch + 127) / 128;
+    size_t blocks = (batch + 63) / 64;
     if (blocks == 0) return HBG_OK;
     if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
-    if (ctx->is_bls)
-      launch_ntt16_f<FieldBLS>(ctx, a, (unsigned)blocks);
-    else
-      launch_ntt16_f<FieldAny>(ctx, a, (unsigned)blocks);
+    rc = ctx->is_bls ? launch_ntt16_f<FieldBLS>(ctx, a) : launch_ntt16_f<FieldAny>(ctx, a);
+    if (rc) return rc;
     CU(cudaGetLastError());
     ctx->launches++;
-    ctx->last_kernel = "ntt16_reg_kernel";
+    ctx->last_kernel = "ntt16_split_kernel";
     return HBG_OK;
   }
   int log_n = ilog2(n);
@@ -415,6 +474,11 @@ int interp_matrix(hbg_ctx* ctx, const std::string& key, int k, const void** d_m,
       for (Fe& v : inv) v = ctx->field->mul(v, r2);
     }
     interleave(inv, k, k, host);
+    if (k <= 8 && !montgomery_out) {
+      std::vector<uint32_t> rm((size_t)k * k * 8);
+      for (int i = 0; i < k * k; i++) memcpy(&rm[(size_t)i * 8], inv[i].w, 32);
+      ctx->host_cache[key] = rm;
+    }
     return HBG_OK;
   });
 }
@@ -704,6 +768,12 @@ int hbg_ctx_synchronize(hbg_ctx* ctx) {
 uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
+int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
+  if (!ctx || path < 0 || path > 3) return HBG_ERR_INVALID;
+  ctx->matvec_path = path;
+  return HBG_OK;
+}
+
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path) {
   if (!ctx || path < 0 || path > 3) return HBG_ERR_INVALID;
   ctx->fft_path = path;
@@ -750,7 +820,8 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
   CU(cudaSetDevice(ctx->device));
   const void* d_m = nullptr;
   // the singularity check must run even for an empty batch (pyx:167-169)
-  int rc = interp_matrix(ctx, make_key("vinv", xs, (size_t)k * 32, nullptr, 0, k), k, &d_m,
+  const std::string key = make_key("vinv", xs, (size_t)k * 32, nullptr, 0, k);
+  int rc = interp_matrix(ctx, key, k, &d_m,
                          [&](std::vector<Fe>& x) { return load_points(ctx, xs, k, x); });
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
@@ -758,7 +829,7 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
   Staged s;
   rc = stage(ctx, ys, batch * (size_t)k * 32, out, batch * (size_t)k * 32, mem, s);
   if (rc) return rc;
-  rc = launch_matvec(ctx, d_m, k, k, s.d_in, k, s.d_out, k, batch);
+  rc = launch_interp(ctx, key, d_m, k, s.d_in, s.d_out, batch);
   if (rc) return rc;
   return unstage(ctx, out, batch * (size_t)k * 32, mem);
 }
@@ -827,7 +898,8 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
   if (k > 4096) return fail(ctx, HBG_ERR_UNSUPPORTED, "interpolation from more than 4096 points");
   CU(cudaSetDevice(ctx->device));
   const void* d_m = nullptr;
-  int rc = interp_matrix(ctx, make_key("finv", omega, 32, zs, (size_t)k * 4, n, k), k, &d_m,
+  const std::string key = make_key("finv", omega, 32, zs, (size_t)k * 4, n, k);
+  int rc = interp_matrix(ctx, key, k, &d_m,
                          [&](std::vector<Fe>& x) {
                            Fe w;
                            int r = check_omega(ctx, omega, n, w);
@@ -846,7 +918,7 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
   Staged s;
   rc = stage(ctx, ys, batch * (size_t)k * 32, out, batch * (size_t)k * 32, mem, s);
   if (rc) return rc;
-  rc = launch_matvec(ctx, d_m, k, k, s.d_in, k, s.d_out, k, batch);
+  rc = launch_interp(ctx, key, d_m, k, s.d_in, s.d_out, batch);
   if (rc) return rc;
   return unstage(ctx, out, batch * (size_t)k * 32, mem);
 }

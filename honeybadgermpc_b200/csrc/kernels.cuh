@@ -167,47 +167,107 @@ __global__ void __launch_bounds__(256) apply_matrix_smem_kernel(MatvecArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// 16-point NTT in registers, one polynomial per thread (the n = 16 encode of
-// the headline config; fft_batch_evaluate with n == 16).  Decimation in
-// frequency, fully unrolled; D = number of input coefficients is a template
-// parameter so structurally-zero operands are dropped at compile time
-// (d = 6: 15 modular multiplications instead of 32).  The 8 twiddles come from
-// the kernel-parameter constant bank.  Output i of the transform sits in slot
-// bitrev4(i).
+// 16-point NTT in registers (the n = 16 encode of the headline config;
+// fft_batch_evaluate with n == 16).  Decimation in frequency, fully unrolled.
+// A polynomial is shared by TWO threads in two different warps: after the first
+// DIF stage the transform splits into two independent 8-point transforms
+//   U_i = c_i + c_{i+8}            -> the even outputs
+//   L_i = (c_i - c_{i+8}) omega^i  -> the odd outputs
+// so warp 2w computes the U halves and warp 2w+1 the L halves of the same 32
+// polynomials (no divergence, no redundant multiplies, twice the parallelism of
+// a thread-per-polynomial mapping -- the batch alone is only ~14 warps per SM).
+// D = number of input coefficients is a template parameter, structurally-zero
+// operands are dropped at compile time (d = 6: 15 modular multiplications per
+// polynomial instead of 32).  The twiddles come from the kernel-parameter
+// constant bank.  Rows are staged through shared memory: TMA bulk copy in,
+// odd-stride tile + coalesced 128-bit stores out.
 // ---------------------------------------------------------------------------
 struct Ntt16Args {
-  const uint4* in;    // [batch][d]
+  const uint4* in;    // [batch][stride]
   uint4* out;         // [batch][k_out]
   unsigned long long batch;
   int d, k_out, stride;  // d <= 16 coefficients used, rows are `stride` elements apart
   uint32_t tw[8][8];      // omega^i, i < 8, Montgomery form
 };
 
-// After s DIF stages slot idx is a combination of the inputs j = idx (mod 16 >> s);
-// with only the first D inputs non-zero it can be non-zero iff (idx mod (16 >> s)) < D.
-#define HB_NTT16_NZ(s, idx, D) ((((idx) & ((16 >> (s)) - 1))) < (D))
-
-template <class F, int D>
-__global__ void __launch_bounds__(128) ntt16_reg_kernel(Ntt16Args a) {
-  unsigned long long b = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
-  if (b >= a.batch) return;
-  Fe v[16];
-  const uint4* src = a.in + 2ull * b * a.stride;  // a.d <= D coefficients per row
-#pragma unroll
-  for (int j = 0; j < 16; j++) {
-    if (j < D) v[j] = j < a.d ? ld_fe(src + 2 * j) : fe_zero();
+// Row-per-thread kernels keep global traffic coalesced by staging through shared
+// memory: the CTA's input rows (one contiguous byte range) arrive with one TMA
+// bulk copy; results are parked in a tile whose row stride is an ODD number of
+// 16-byte chunks (conflict-free for lane-per-row writes) and then streamed out
+// by all threads with consecutive 128-bit stores.
+template <int THREADS>
+HB_D void tile_store_rows(uint4* tile, uint4* gout, int rows_here, int chunks_per_row) {
+  const int total = rows_here * chunks_per_row;
+  const int pstride = chunks_per_row | 1;  // odd
+  for (int q = threadIdx.x; q < total; q += THREADS) {
+    int r = q / chunks_per_row, c = q - r * chunks_per_row;
+    gout[q] = tile[r * pstride + c];
   }
+}
+
+// within the 8-point transform: after s stages slot idx depends on the inputs
+// j = idx (mod 8 >> s); with the first D8 inputs non-zero it is non-zero iff that
+// residue is < D8
+#define HB_NTT8_NZ(s, idx, D8) ((((idx) & ((8 >> (s)) - 1))) < (D8))
+
+template <class F, int D, int POLYS>
+__global__ void __launch_bounds__(2 * POLYS) ntt16_split_kernel(const __grid_constant__ Ntt16Args a) {
+  extern __shared__ uint4 smem[];
+  __shared__ alignas(8) uint64_t bar;
+  constexpr int D8 = D < 8 ? D : 8;
+  const unsigned long long row0 = (unsigned long long)blockIdx.x * POLYS;
+  unsigned long long left = a.batch - row0;
+  const int rows_here = left < (unsigned long long)POLYS ? (int)left : POLYS;
+  const bool dense = a.stride == a.d;  // contiguous input rows: one bulk copy
+  if (dense) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      tma_load_1d(smem, a.in + 2ull * row0 * a.stride, (unsigned)rows_here * a.d * 32u, &bar);
+    mbar_wait(&bar, 0);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp & 1;                  // 0: U (even outputs), 1: L (odd outputs)
+  const int poly = (warp >> 1) * 32 + lane;   // row within the CTA
+  const bool active = poly < rows_here;
+  Fe v[8];
+  {
+    const uint4* src = dense ? smem + 2 * poly * a.d : a.in + 2ull * (row0 + poly) * a.stride;
 #pragma unroll
-  for (int s = 1; s <= 4; s++) {
-    const int h = 16 >> s;
+    for (int i = 0; i < 8; i++) {
+      if (i >= D8) continue;
+      Fe lo = (active && i < a.d) ? ld_fe(src + 2 * i) : fe_zero();
+      if (i + 8 < D) {
+        Fe hi = (active && i + 8 < a.d) ? ld_fe(src + 2 * (i + 8)) : fe_zero();
+        v[i] = half ? fe_sub<F>(lo, hi) : fe_add<F>(lo, hi);
+      } else {
+        v[i] = lo;
+      }
+    }
+  }
+  __syncthreads();  // the input tile is dead: its space becomes the output tile
+  if (half) {
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
+    for (int i = 1; i < 8; i++) {
+      if (i >= D8) continue;
+      Fe w;
+#pragma unroll
+      for (int q = 0; q < 8; q++) w.w[q] = a.tw[i][q];
+      v[i] = mont_mul<F>(v[i], w);
+    }
+  }
+  // 8-point DIF on omega^2
+#pragma unroll
+  for (int s = 1; s <= 3; s++) {
+    const int h = 8 >> s;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
       const int pos = t & (h - 1);
       const int i0 = ((t & ~(h - 1)) << 1) | pos;
       const int i1 = i0 + h;
-      const bool nz0 = HB_NTT16_NZ(s - 1, i0, D), nz1 = HB_NTT16_NZ(s - 1, i1, D);
+      const bool nz0 = HB_NTT8_NZ(s - 1, i0, D8), nz1 = HB_NTT8_NZ(s - 1, i1, D8);
       if (!nz0 && !nz1) continue;
-      const int tw_idx = pos << (s - 1);  // omega^(pos * 2^(s-1))
+      const int tw_idx = (pos << (s - 1)) * 2;  // (omega^2)^(pos * 2^(s-1))
       Fe lo, hi;
       if (!nz1) {
         lo = v[i0];
@@ -229,12 +289,67 @@ __global__ void __launch_bounds__(128) ntt16_reg_kernel(Ntt16Args a) {
       v[i1] = hi;
     }
   }
-  uint4* dst = a.out + 2ull * b * a.k_out;
+  // slot idx of half h holds X[2 * bitrev3(idx) + h]
+  const int chunks = 2 * a.k_out, pstride = chunks | 1;
+  uint4* mine = smem + poly * pstride;
 #pragma unroll
-  for (int idx = 0; idx < 16; idx++) {
-    const int i = ((idx & 1) << 3) | ((idx & 2) << 1) | ((idx & 4) >> 1) | ((idx & 8) >> 3);
-    if (i < a.k_out) st_fe(dst + 2 * i, v[idx]);
+  for (int idx = 0; idx < 8; idx++) {
+    const int i = 2 * (((idx & 1) << 2) | (idx & 2) | ((idx & 4) >> 2)) + half;
+    if (i < a.k_out) st_fe(mine + 2 * i, v[idx]);
   }
+  __syncthreads();
+  tile_store_rows<2 * POLYS>(smem, a.out + 2ull * row0 * a.k_out, rows_here, chunks);
+}
+
+// ---------------------------------------------------------------------------
+// Small square interpolation (k <= 8), one row per thread: the k x k matrix
+// V(x)^-1 sits in the kernel-parameter constant bank, so its limbs are direct
+// IMAD.WIDE operands (no loads, no registers); the k inputs of the row stay in
+// registers for all k outputs.  vandermonde_batch_interpolate and
+// fft_batch_interpolate of the headline config (k = t+1 = 6) run here.
+// ---------------------------------------------------------------------------
+template <int K>
+struct SmallInterpArgs {
+  const uint4* in;    // [batch][K]
+  uint4* out;         // [batch][K]
+  unsigned long long batch;
+  uint32_t m[K][K][8];  // M[i][j], Montgomery form
+};
+
+template <class F, int K, int THREADS>
+__global__ void __launch_bounds__(THREADS) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
+  extern __shared__ uint4 smem[];
+  __shared__ alignas(8) uint64_t bar;
+  const unsigned long long row0 = (unsigned long long)blockIdx.x * THREADS;
+  unsigned long long left = a.batch - row0;
+  const int rows_here = left < (unsigned long long)THREADS ? (int)left : THREADS;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tma_load_1d(smem, a.in + 2ull * row0 * K, (unsigned)rows_here * K * 32u, &bar);
+  mbar_wait(&bar, 0);
+  const bool active = (int)threadIdx.x < rows_here;
+  Fe y[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) y[j] = active ? ld_fe(smem + 2 * (threadIdx.x * K + j)) : fe_zero();
+  __syncthreads();
+  constexpr int pstride = (2 * K) | 1;
+  uint4* mine = smem + threadIdx.x * pstride;
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    Acc acc;
+    acc_zero(acc);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      Fe m;
+#pragma unroll
+      for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
+      acc_mac(acc, y[j], m);
+      if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
+    }
+    st_fe(mine + 2 * i, acc_redc<F>(acc));
+  }
+  __syncthreads();
+  tile_store_rows<THREADS>(smem, a.out + 2ull * row0 * K, rows_here, 2 * K);
 }
 
 // ---------------------------------------------------------------------------

@@ -76,6 +76,12 @@ const char* hbg_ctx_last_kernel(const hbg_ctx* ctx);
  * 1 = dot products, 2 = butterflies, 3 = butterflies through the generic
  * shared-memory kernel even where a register-resident kernel exists (n = 16). */
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path);
+/* Which dot-product kernel applies a matrix to the batch (results are
+ * bit-identical): 0 = pick by size (default), 1 = matrix read through L1 from
+ * global memory, 2 = matrix and TMA-staged input tile in shared memory,
+ * 3 = k <= 8 interpolation with the matrix in the constant bank, one row per
+ * thread (falls back to 0 where it does not apply). */
+int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path);
 
 /* vandermonde_batch_evaluate(x, polynomials, modulus), pyx:199-244 +
  * set_vm_matrix rsdecode_impl.h:23-36:

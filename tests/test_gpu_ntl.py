@@ -79,7 +79,8 @@ def test_interpolate_at_zero(ntl, golden):
 
 @pytest.mark.parametrize("p", [P, 13, 53, 2 ** 127 - 1])
 @pytest.mark.parametrize("n,d,batch", [(1, 1, 1), (4, 2, 128), (16, 6, 257), (16, 16, 33),
-                                       (7, 3, 5), (64, 22, 40), (128, 43, 9)])
+                                       (7, 3, 5), (64, 22, 40), (128, 43, 9), (8, 8, 300), (5, 5, 129),
+                                       (9, 7, 64), (3, 1, 7)])
 def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
     rng = random.Random(n * 1000 + d)
     if p <= n:
@@ -88,14 +89,19 @@ def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
         xs = list(range(1, n + 1))
     polys = [[rng.randrange(p) for _ in range(rng.randint(1, d))] for _ in range(batch)]
     polys[0] = polys[0] + [p - 1] * (d - len(polys[0]))
-    got = ntl.vandermonde_batch_evaluate(xs, polys, p)
-    assert got == orc.vandermonde_batch_evaluate(xs, polys, p)
+    want = orc.vandermonde_batch_evaluate(xs, polys, p)
+    for path in ("auto", "global", "smem", "small"):
+        ntl._ctx(p).set_matvec_path(path)
+        assert ntl.vandermonde_batch_evaluate(xs, polys, p) == want, path
     if p > n:
         k = d
         xk = rng.sample(xs, k)
         ys = [[rng.randrange(p) for _ in range(k)] for _ in range(batch)]
-        assert ntl.vandermonde_batch_interpolate(xk, ys, p) == \
-            orc.vandermonde_batch_interpolate(xk, ys, p)
+        want = orc.vandermonde_batch_interpolate(xk, ys, p)
+        for path in ("auto", "global", "smem", "small"):
+            ntl._ctx(p).set_matvec_path(path)
+            assert ntl.vandermonde_batch_interpolate(xk, ys, p) == want, path
+    ntl._ctx(p).set_matvec_path("auto")
 
 
 def test_worst_case_values(ntl):
