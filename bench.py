@@ -199,9 +199,34 @@ def run_b200(args):
             y.append(ys)
             r.append(torch.zeros((batch, K, 4), dtype=torch.int64, device=dev))
         depth = min(3, sets)
-        gathered = [torch.empty((world * batch, K, 4), dtype=torch.int64, device=dev)
-                    for _ in range(depth)] if world > 1 else []
+        gathered, handles, gather_mode = [], [], "none"
+        if world > 1 and args.gather != "nccl":
+            # symmetric memory: every rank's gather buffer mapped into every process, plus an
+            # NVSwitch multicast address when the fabric offers one -> the interpolation kernel
+            # stores its block straight into all ranks' buffers (fused compute + all-gather)
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                for _ in range(depth):
+                    buf = symm_mem.empty((world * batch, K, 4), dtype=torch.int64, device=dev)
+                    handles.append(symm_mem.rendezvous(buf, dist.group.WORLD))
+                    gathered.append(buf)
+                mc = int(getattr(handles[0], "multicast_ptr", 0) or 0)
+                if args.gather == "p2p":
+                    mc = 0
+                gather_mode = "fused-multimem" if mc else "fused-p2p"
+            except Exception as exc:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({exc!r}); using NCCL all-gather",
+                          file=sys.stderr)
+                gathered, handles = [], []
+        if world > 1 and not handles:
+            gather_mode = "nccl-overlapped"
+            gathered = [torch.empty((world * batch, K, 4), dtype=torch.int64, device=dev)
+                        for _ in range(depth)]
         pending = [None] * len(gathered)
+        slot_done = [None] * len(gathered)
+        side = torch.cuda.Stream(device=dev)
     stream.synchronize()
 
     names = {}
@@ -215,13 +240,34 @@ def run_b200(args):
             names["encode"] = ctx.last_kernel()
         if evs is not None:
             evs[1].record(stream)
-        ctx.fft_batch_interpolate(omega, pt.order, ZS, y[s].data_ptr(), batch, r[s].data_ptr(),
-                                  _native.MEM_DEVICE)
+        if handles:
+            slot = s % len(gathered)
+            h = handles[slot]
+            if slot_done[slot] is not None:
+                stream.wait_event(slot_done[slot])  # the previous gather into this slot is complete everywhere
+            use_mc = int(getattr(h, "multicast_ptr", 0) or 0) if gather_mode == "fused-multimem" else 0
+            ctx.fft_batch_interpolate_allgather(omega, pt.order, ZS, y[s].data_ptr(), batch,
+                                                list(h.buffer_ptrs), use_mc, rank)
+        else:
+            ctx.fft_batch_interpolate(omega, pt.order, ZS, y[s].data_ptr(), batch, r[s].data_ptr(),
+                                      _native.MEM_DEVICE)
         if "interpolate" not in names:
             names["interpolate"] = ctx.last_kernel()
         if evs is not None:
             evs[2].record(stream)
-        if world > 1:
+        if handles:
+            # completion of the gather (= every rank's block has landed in every buffer) is a
+            # device-side barrier over the symmetric-memory signal pads; it runs on a side
+            # stream so this rank's next encode does not wait for the slowest rank
+            slot = s % len(gathered)
+            written = torch.cuda.Event()
+            written.record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(written)
+                handles[slot].barrier()
+                slot_done[slot] = torch.cuda.Event()
+                slot_done[slot].record(side)
+        elif world > 1:
             # the one collective of the path: reassemble the decoded blocks on every rank.
             # It runs on NCCL's stream and overlaps the next step's kernels; the buffer
             # pair (r[s], gathered[slot]) is only reused after its gather has completed.
@@ -268,11 +314,22 @@ def run_b200(args):
     dec_ms = sum(ev[1].elapsed_time(ev[2]) for ev in evs) / args.steps
 
     # parity inside the bench: every decoded block equals its coefficients
-    for s in range(min(sets, args.warmup + args.steps)):
-        assert torch.equal(r[s], c[s]), f"round trip mismatch in buffer set {s}"
-    if world > 1:
+    used = min(sets, args.warmup + args.steps)
+    if handles:
         last = (args.warmup + args.steps - 1) % sets
-        assert torch.equal(gathered[last % len(gathered)][rank * batch:(rank + 1) * batch], r[last])
+        g = gathered[last % len(gathered)]
+        assert torch.equal(g[rank * batch:(rank + 1) * batch], c[last]), "fused gather: own block mismatch"
+        sums = g.view(world, -1).sum(dim=1)
+        lo, hi = sums.clone(), sums.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "fused gather: ranks disagree on the gathered blocks"
+    else:
+        for s in range(used):
+            assert torch.equal(r[s], c[s]), f"round trip mismatch in buffer set {s}"
+        if world > 1:
+            last = (args.warmup + args.steps - 1) % sets
+            assert torch.equal(gathered[last % len(gathered)][rank * batch:(rank + 1) * batch], r[last])
 
     ms_per_step = total_ms / args.steps
     value = world * batch * K / (ms_per_step * 1e-3)
@@ -371,7 +428,7 @@ def run_b200(args):
                        "field": "BLS12-381 r", "z": ZS,
                        "l2": f"{sets} rotating buffer sets of {(enc_bytes + dec_bytes) / 1e6:.0f} MB "
                              "(inputs+outputs larger than the 126 MB L2)",
-                       "parallelism": f"batch shard x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                       "parallelism": f"batch shard x{world}" + (f" + all-gather ({gather_mode})" if world > 1 else ""),
                        "polys_per_s": value / K},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.result(),
@@ -392,6 +449,9 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--sets", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1: fused stores into symmetric memory (multicast if available), "
+                         "peer stores only, or an overlapped NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -71,6 +71,11 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]),
+    "hbg_fft_batch_interpolate_allgather": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+         ctypes.c_int]),
     "hbg_gao_decode_batch": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -202,6 +207,14 @@ class Context:
         self._check(self.lib.hbg_fft_batch_interpolate(
             self.handle, _ptr(omega), n, _ptr(zs), len(zs), _ptr(ys), batch, _ptr(out), mem))
 
+
+    def fft_batch_interpolate_allgather(self, omega, n, zs, ys, batch, peer_ptrs, multicast_ptr, rank):
+        """device pointers only; peer_ptrs: one pointer per rank (ints)"""
+        zs = np.ascontiguousarray(zs, dtype=np.int32)
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.hbg_fft_batch_interpolate_allgather(
+            self.handle, _ptr(omega), n, _ptr(zs), len(zs), _ptr(ys), batch, arr,
+            int(multicast_ptr) if multicast_ptr else None, len(peer_ptrs), rank))
 
     def gao_decode_batch(self, xs, k, ys, batch, coeffs, locator, loc_stride, loc_len, status,
                          mem=MEM_HOST):

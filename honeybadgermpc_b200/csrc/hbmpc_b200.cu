@@ -322,12 +322,18 @@ int launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a) {
 // k x k interpolation with the matrix in the kernel-parameter constant bank
 template <class F, int K>
 int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const void* d_in, void* d_out,
-                          size_t batch) {
+                          size_t batch, const GatherDst* gather, size_t gather_row0) {
   constexpr int T = 128;
   SmallInterpArgs<K> a;
   a.in = (const uint4*)d_in;
   a.out = (uint4*)d_out;
   a.batch = batch;
+  a.gather_row0 = gather_row0;
+  if (gather) {
+    a.gather = *gather;
+  } else {
+    memset(&a.gather, 0, sizeof(a.gather));
+  }
   memcpy(a.m, m.data(), sizeof(a.m));
   const size_t in_tile = (size_t)T * K * 32, out_tile = (size_t)T * ((2 * K) | 1) * 16;
   const size_t smem = in_tile > out_tile ? in_tile : out_tile;
@@ -337,16 +343,17 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
 
 template <class F>
 int launch_interp_small_f(hbg_ctx* ctx, int k, const std::vector<uint32_t>& m, const void* d_in,
-                          void* d_out, size_t batch) {
+                          void* d_out, size_t batch, const GatherDst* gather = nullptr,
+                          size_t gather_row0 = 0) {
   switch (k) {
-    case 1: return launch_interp_small_t<F, 1>(ctx, m, d_in, d_out, batch);
-    case 2: return launch_interp_small_t<F, 2>(ctx, m, d_in, d_out, batch);
-    case 3: return launch_interp_small_t<F, 3>(ctx, m, d_in, d_out, batch);
-    case 4: return launch_interp_small_t<F, 4>(ctx, m, d_in, d_out, batch);
-    case 5: return launch_interp_small_t<F, 5>(ctx, m, d_in, d_out, batch);
-    case 6: return launch_interp_small_t<F, 6>(ctx, m, d_in, d_out, batch);
-    case 7: return launch_interp_small_t<F, 7>(ctx, m, d_in, d_out, batch);
-    case 8: return launch_interp_small_t<F, 8>(ctx, m, d_in, d_out, batch);
+    case 1: return launch_interp_small_t<F, 1>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 2: return launch_interp_small_t<F, 2>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 3: return launch_interp_small_t<F, 3>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 4: return launch_interp_small_t<F, 4>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 5: return launch_interp_small_t<F, 5>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 6: return launch_interp_small_t<F, 6>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 7: return launch_interp_small_t<F, 7>(ctx, m, d_in, d_out, batch, gather, gather_row0);
+    case 8: return launch_interp_small_t<F, 8>(ctx, m, d_in, d_out, batch, gather, gather_row0);
   }
   return HBG_ERR_UNSUPPORTED;
 }
@@ -832,6 +839,54 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
   rc = launch_interp(ctx, key, d_m, k, s.d_in, s.d_out, batch);
   if (rc) return rc;
   return unstage(ctx, out, batch * (size_t)k * 32, mem);
+}
+
+int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], int n, const int32_t* zs,
+                                        int k, const uint64_t* ys, size_t batch, void* const* peer_out,
+                                        void* multicast_out, int world, int rank) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!omega || k < 1 || !zs || !ys || !peer_out || world < 1 || world > 8 || rank < 0 || rank >= world)
+    return fail(ctx, HBG_ERR_INVALID, "bad argument");
+  if (k > 8) return fail(ctx, HBG_ERR_UNSUPPORTED, "fused all-gather is implemented for k <= 8");
+  CU(cudaSetDevice(ctx->device));
+  const void* d_m = nullptr;
+  const std::string key = make_key("finv", omega, 32, zs, (size_t)k * 4, n, k);
+  int rc = interp_matrix(ctx, key, k, &d_m,
+                         [&](std::vector<Fe>& x) {
+                           Fe w;
+                           int r = check_omega(ctx, omega, n, w);
+                           if (r) return r;
+                           x.resize(k);
+                           for (int i = 0; i < k; i++) {
+                             if (zs[i] < 0 || zs[i] >= n)
+                               return fail(ctx, HBG_ERR_INVALID, "z outside [0, n)");
+                             x[i] = ctx->field->pow_u64(w, (uint64_t)zs[i]);
+                           }
+                           return HBG_OK;
+                         });
+  if (rc) return rc;
+  if (batch == 0) return HBG_OK;
+  auto it = ctx->host_cache.find(key);
+  if (it == ctx->host_cache.end()) return fail(ctx, HBG_ERR_UNSUPPORTED, "matrix not cached on host");
+  GatherDst g;
+  memset(&g, 0, sizeof(g));
+  g.world = world;
+  g.mc = (uint4*)multicast_out;
+  for (int r = 0; r < world; r++) {
+    if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
+    g.peers[r] = (uint4*)peer_out[r];
+  }
+  rc = bind_field(ctx);
+  if (rc) return rc;
+  rc = ctx->is_bls ? launch_interp_small_f<FieldBLS>(ctx, k, it->second, ys, nullptr, batch, &g,
+                                                     (size_t)rank * batch)
+                   : launch_interp_small_f<FieldAny>(ctx, k, it->second, ys, nullptr, batch, &g,
+                                                     (size_t)rank * batch);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "interp_small_kernel";
+  return HBG_OK;
 }
 
 int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const uint64_t* polys,

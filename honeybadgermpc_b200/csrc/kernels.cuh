@@ -205,6 +205,38 @@ HB_D void tile_store_rows(uint4* tile, uint4* gout, int rows_here, int chunks_pe
   }
 }
 
+// Fused all-gather: instead of one local destination the result tile is stored
+// into every rank's gather buffer through NVLink-mapped peer pointers, or -- when
+// the buffers are bound to an NVSwitch multicast object -- with ONE multimem.st
+// per 16 bytes that the switch replicates to all ranks.
+struct GatherDst {
+  uint4* peers[8];   // peer-mapped base pointers of every rank's [world*batch][k] array
+  uint4* mc;         // multicast address of the same buffers, or null
+  int world;
+};
+
+HB_D void st_multimem(uint4* p, const uint4& v) {
+  asm volatile("multimem.st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+template <int THREADS>
+HB_D void tile_store_rows_gather(uint4* tile, const GatherDst& g, unsigned long long chunk0, int rows_here,
+                                 int chunks_per_row) {
+  const int total = rows_here * chunks_per_row;
+  const int pstride = chunks_per_row | 1;
+  for (int q = threadIdx.x; q < total; q += THREADS) {
+    int r = q / chunks_per_row, c = q - r * chunks_per_row;
+    uint4 v = tile[r * pstride + c];
+    if (g.mc) {
+      st_multimem(g.mc + chunk0 + q, v);
+    } else {
+      for (int w = 0; w < g.world; w++) g.peers[w][chunk0 + q] = v;
+    }
+  }
+}
+
 // within the 8-point transform: after s stages slot idx depends on the inputs
 // j = idx (mod 8 >> s); with the first D8 inputs non-zero it is non-zero iff that
 // residue is < D8
@@ -313,7 +345,9 @@ struct SmallInterpArgs {
   const uint4* in;    // [batch][K]
   uint4* out;         // [batch][K]
   unsigned long long batch;
-  uint32_t m[K][K][8];  // M[i][j], Montgomery form
+  unsigned long long gather_row0;  // first row of this rank inside the gathered array
+  GatherDst gather;                // world == 0: plain local output
+  uint32_t m[K][K][8];             // M[i][j], Montgomery form
 };
 
 template <class F, int K, int THREADS>
@@ -349,7 +383,10 @@ __global__ void __launch_bounds__(THREADS) interp_small_kernel(const __grid_cons
     st_fe(mine + 2 * i, acc_redc<F>(acc));
   }
   __syncthreads();
-  tile_store_rows<THREADS>(smem, a.out + 2ull * row0 * K, rows_here, 2 * K);
+  if (a.gather.world > 0)
+    tile_store_rows_gather<THREADS>(smem, a.gather, 2ull * (a.gather_row0 + row0) * K, rows_here, 2 * K);
+  else
+    tile_store_rows<THREADS>(smem, a.out + 2ull * row0 * K, rows_here, 2 * K);
 }
 
 // ---------------------------------------------------------------------------

@@ -119,6 +119,22 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n,
                               const uint64_t* ys, size_t batch,
                               uint64_t* out, int mem);
 
+/* hbg_fft_batch_interpolate fused with the all-gather of the multi-GPU path
+ * (one rank per GPU, the batch axis sharded): the decoded
+ * block of this rank -- rows [rank*batch, (rank+1)*batch) of the gathered
+ * [world*batch][k] array -- is written from inside the interpolation kernel
+ * straight into EVERY rank's gather buffer.  peer_out[r] is rank r's buffer as
+ * mapped into this process (peer / symmetric-memory pointer; peer_out[rank] is
+ * the local one).  If multicast_out is non-NULL it is an NVSwitch multicast
+ * address bound to all of these buffers and each 16-byte store is issued once
+ * (multimem.st) and replicated by the switch.  Device pointers only (ys too);
+ * k <= 8.  The caller synchronises the ranks before reading the buffers. */
+int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], int n,
+                                        const int32_t* zs, int k,
+                                        const uint64_t* ys, size_t batch,
+                                        void* const* peer_out, void* multicast_out,
+                                        int world, int rank);
+
 /* gao_interpolate(x, y, k, modulus, ...), pyx:389-439 + gao_interpolate /
  * gao_interpolate_fft / partial_gcd, rsdecode_impl.h:281-405 -- batched: every
  * row of ys is one received word on the SAME m points xs (erasures already

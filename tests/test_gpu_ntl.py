@@ -193,3 +193,25 @@ def test_empty_and_ragged(ntl):
     assert ntl.evaluate([], 5, P) == 0
     assert ntl.lagrange_interpolate([], [], P) == []
     assert ntl.fft([], ROOTS_OF_UNITY[2], P, 4) == [0, 0, 0, 0]
+
+
+def test_fused_allgather_world1(ntl):
+    """hbg_fft_batch_interpolate_allgather with a single rank: the block lands at
+    rank*batch of the 'gathered' buffer (the multi-rank form is exercised by
+    bench.py --gpus N, which asserts the same on every rank)."""
+    import torch
+
+    n, k, batch = 16, 6, 1000
+    pt = orc.EvalPoint(P, n, True)
+    rng = np.random.default_rng(3)
+    c = rng.integers(0, 2 ** 62, size=(batch, k, 4), dtype=np.uint64)
+    omega = ntl.pack_vec([pt.omega], P)[0]
+    enc = ntl.fft_batch_evaluate_limbs(c, omega, P, pt.order, n)
+    zs = [0, 2, 5, 7, 11, 13]
+    ys = torch.from_numpy(np.ascontiguousarray(enc[:, zs, :]).view(np.int64)).cuda()
+    out = torch.zeros((batch, k, 4), dtype=torch.int64, device="cuda")
+    ctx = ntl._ctx(P)
+    torch.cuda.synchronize()
+    ctx.fft_batch_interpolate_allgather(omega, pt.order, zs, ys.data_ptr(), batch, [out.data_ptr()], 0, 0)
+    ctx.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), c)
