@@ -49,6 +49,8 @@ struct hbg_ctx {
   uint64_t launches = 0;
   const char* last_kernel = "";
   DevBuf in, out, work, work2;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // host-buffer pipeline: H2D / D2H streams
+  cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
   int sm_count = 148;
   std::unordered_map<std::string, DevConst> cache;
   std::unordered_map<std::string, std::vector<uint32_t>> host_cache;  // small tables passed by value
@@ -169,32 +171,61 @@ void interleave(const std::vector<Fe>& m, int rows, int cols, std::vector<uint32
         out[((size_t)j * 8 + w) * rows + i] = m[(size_t)i * cols + j].w[w];
 }
 
-struct Staged {
-  const void* d_in = nullptr;
-  void* d_out = nullptr;
-};
-
-int stage(hbg_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes, int mem,
-          Staged& s) {
-  if (mem == HBG_MEM_DEVICE) {
-    s.d_in = in;
-    s.d_out = out;
+// Row-wise batch operation with HOST buffers: the batch is cut into up to 8 chunks
+// and H2D copy / kernel / D2H copy of consecutive chunks overlap on three streams
+// (PCIe is full duplex), so the call costs about max(bytes in, bytes out) / PCIe
+// rate instead of their sum.  DEVICE buffers: just the launch.
+template <class Launch>
+int run_rows(hbg_ctx* ctx, const void* in, size_t in_row, void* out, size_t out_row, size_t batch,
+             int mem, Launch launch) {
+  if (mem == HBG_MEM_DEVICE) return launch(in, out, batch);
+  if (mem != HBG_MEM_HOST) return fail(ctx, HBG_ERR_INVALID, "mem must be HBG_MEM_HOST or HBG_MEM_DEVICE");
+  int rc = ensure(ctx, ctx->in, batch * in_row);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->out, batch * out_row);
+  if (rc) return rc;
+  size_t chunks = batch * (in_row + out_row) >= ((size_t)4 << 20) ? 8 : 1;
+  if (chunks > batch) chunks = 1;
+  if (chunks == 1) {
+    if (in_row) CU(cudaMemcpyAsync(ctx->in.p, in, batch * in_row, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch(ctx->in.p, ctx->out.p, batch);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, ctx->out.p, batch * out_row, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return HBG_OK;
   }
-  if (mem != HBG_MEM_HOST) return fail(ctx, HBG_ERR_INVALID, "mem must be HBG_MEM_HOST or HBG_MEM_DEVICE");
-  int rc = ensure(ctx, ctx->in, in_bytes);
-  if (rc) return rc;
-  rc = ensure(ctx, ctx->out, out_bytes);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  s.d_in = ctx->in.p;
-  s.d_out = ctx->out.p;
-  return HBG_OK;
-}
-
-int unstage(hbg_ctx* ctx, void* out, size_t out_bytes, int mem) {
-  if (mem == HBG_MEM_DEVICE) return HBG_OK;
-  CU(cudaMemcpyAsync(out, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!ctx->s_in) {
+    CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+      CU(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t per = (batch + chunks - 1) / chunks;
+  for (size_t i = 0; i < chunks; i++) {
+    const size_t r0 = i * per;
+    if (r0 >= batch) break;
+    const size_t rows = batch - r0 < per ? batch - r0 : per;
+    uint8_t* d_in = (uint8_t*)ctx->in.p + r0 * in_row;
+    uint8_t* d_out = (uint8_t*)ctx->out.p + r0 * out_row;
+    CU(cudaMemcpyAsync(d_in, (const uint8_t*)in + r0 * in_row, rows * in_row, cudaMemcpyHostToDevice,
+                       ctx->s_in));
+    CU(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+    rc = launch(d_in, d_out, rows);
+    if (rc) {
+      cudaStreamSynchronize(ctx->s_in);
+      cudaStreamSynchronize(ctx->stream);
+      cudaStreamSynchronize(ctx->s_out);
+      return rc;
+    }
+    CU(cudaEventRecord(ctx->ev_k[i], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[i], 0));
+    CU(cudaMemcpyAsync((uint8_t*)out + r0 * out_row, d_out, rows * out_row, cudaMemcpyDeviceToHost,
+                       ctx->s_out));
+  }
+  CU(cudaStreamSynchronize(ctx->s_out));
   CU(cudaStreamSynchronize(ctx->stream));
   return HBG_OK;
 }
@@ -228,7 +259,7 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
   if (rc) return rc;
   const size_t m_bytes = (size_t)n_out * d * 32;
   const size_t tile_bytes = (size_t)a.rows_per_cta * d * 32;
-  if (ctx->matvec_path != 1 && n_out <= 256 && d >= 1 && in_stride == d && m_bytes <= 48 * 1024 &&
+  if (ctx->matvec_path != 1 && n_out <= 256 && d >= 1 && in_stride == d && m_bytes <= 100 * 1024 &&
       tile_bytes <= 64 * 1024) {
     size_t smem = m_bytes + tile_bytes;
     if (ctx->is_bls) {
@@ -690,11 +721,11 @@ int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_ma
   if (ctx->is_bls) {
     rc = allow_big_smem(ctx, wb_kernel<FieldBLS>);
     if (rc) return rc;
-    wb_kernel<FieldBLS><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+    wb_kernel<FieldBLS><<<(unsigned)blocks, kWbThreads, smem, ctx->stream>>>(a);
   } else {
     rc = allow_big_smem(ctx, wb_kernel<FieldAny>);
     if (rc) return rc;
-    wb_kernel<FieldAny><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
+    wb_kernel<FieldAny><<<(unsigned)blocks, kWbThreads, smem, ctx->stream>>>(a);
   }
   CU(cudaGetLastError());
   ctx->launches++;
@@ -753,6 +784,14 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->out.p) cudaFree(ctx->out.p);
   if (ctx->work.p) cudaFree(ctx->work.p);
   if (ctx->work2.p) cudaFree(ctx->work2.p);
+  if (ctx->s_in) {
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 8; i++) {
+      cudaEventDestroy(ctx->ev_in[i]);
+      cudaEventDestroy(ctx->ev_k[i]);
+    }
+  }
   cudaStreamDestroy(ctx->own_stream);
   delete ctx->field;
   delete ctx;
@@ -812,12 +851,10 @@ int hbg_vandermonde_batch_evaluate(hbg_ctx* ctx, const uint64_t* xs, int n, cons
                        return HBG_OK;
                      });
   if (rc) return rc;
-  Staged s;
-  rc = stage(ctx, polys, batch * (size_t)d * 32, out, batch * (size_t)n * 32, mem, s);
-  if (rc) return rc;
-  rc = launch_matvec(ctx, d_m, n, d, s.d_in, d, s.d_out, n, batch);
-  if (rc) return rc;
-  return unstage(ctx, out, batch * (size_t)n * 32, mem);
+  return run_rows(ctx, polys, (size_t)d * 32, out, (size_t)n * 32, batch, mem,
+                  [&](const void* di, void* dout, size_t rows) {
+                    return launch_matvec(ctx, d_m, n, d, di, d, dout, n, rows);
+                  });
 }
 
 int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, const uint64_t* ys,
@@ -833,12 +870,10 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
   if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
-  Staged s;
-  rc = stage(ctx, ys, batch * (size_t)k * 32, out, batch * (size_t)k * 32, mem, s);
-  if (rc) return rc;
-  rc = launch_interp(ctx, key, d_m, k, s.d_in, s.d_out, batch);
-  if (rc) return rc;
-  return unstage(ctx, out, batch * (size_t)k * 32, mem);
+  return run_rows(ctx, ys, (size_t)k * 32, out, (size_t)k * 32, batch, mem,
+                  [&](const void* di, void* dout, size_t rows) {
+                    return launch_interp(ctx, key, d_m, k, di, dout, rows);
+                  });
 }
 
 int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], int n, const int32_t* zs,
@@ -910,11 +945,10 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   if (ctx->fft_path == 1 && (size_t)k_out * d_eff <= (1u << 22)) use_matrix = true;
   if (ctx->fft_path >= 2 && n >= 2) use_matrix = false;
   if ((size_t)k_out * d_eff > (1u << 22)) use_matrix = false;
-  Staged s;
-  rc = stage(ctx, polys, batch * (size_t)d * 32, out, batch * (size_t)k_out * 32, mem, s);
-  if (rc) return rc;
+  const void* d_m = nullptr;
+  const void* d_tw = nullptr;
+  const std::vector<uint32_t>* h_tw = nullptr;
   if (use_matrix) {
-    const void* d_m = nullptr;
     rc = get_const(ctx, make_key("dft", omega, 32, &n, sizeof n, k_out, d_eff), &d_m,
                    [&](std::vector<uint32_t>& host) {
                      Fe w;
@@ -933,17 +967,15 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
                      interleave(m, k_out, d_eff, host);
                      return HBG_OK;
                    });
-    if (rc) return rc;
-    rc = launch_matvec(ctx, d_m, k_out, d_eff, s.d_in, d, s.d_out, k_out, batch);
   } else {
-    const void* d_tw = nullptr;
-    const std::vector<uint32_t>* h_tw = nullptr;
     rc = twiddles(ctx, omega, n, &d_tw, &h_tw);
-    if (rc) return rc;
-    rc = launch_ntt(ctx, d_tw, h_tw, n, s.d_in, d, s.d_out, k_out, batch);
   }
   if (rc) return rc;
-  return unstage(ctx, out, batch * (size_t)k_out * 32, mem);
+  return run_rows(ctx, polys, (size_t)d * 32, out, (size_t)k_out * 32, batch, mem,
+                  [&](const void* di, void* dout, size_t rows) {
+                    if (use_matrix) return launch_matvec(ctx, d_m, k_out, d_eff, di, d, dout, k_out, rows);
+                    return launch_ntt(ctx, d_tw, h_tw, n, di, d, dout, k_out, rows);
+                  });
 }
 
 int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, const int32_t* zs, int k,
@@ -970,12 +1002,10 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
   if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
-  Staged s;
-  rc = stage(ctx, ys, batch * (size_t)k * 32, out, batch * (size_t)k * 32, mem, s);
-  if (rc) return rc;
-  rc = launch_interp(ctx, key, d_m, k, s.d_in, s.d_out, batch);
-  if (rc) return rc;
-  return unstage(ctx, out, batch * (size_t)k * 32, mem);
+  return run_rows(ctx, ys, (size_t)k * 32, out, (size_t)k * 32, batch, mem,
+                  [&](const void* di, void* dout, size_t rows) {
+                    return launch_interp(ctx, key, d_m, k, di, dout, rows);
+                  });
 }
 
 }  // extern "C"

@@ -245,8 +245,10 @@ struct WbArgs {
   int in_smem;
 };
 
+constexpr int kWbThreads = 512;  // 16 warps per CTA: one CTA per SM when the system fills shared memory
+
 template <class F>
-__global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
+__global__ void __launch_bounds__(kWbThreads) wb_kernel(WbArgs a) {
   extern __shared__ uint4 smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int m = a.m, k = a.k;
@@ -282,14 +284,14 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
 
   for (unsigned long long row = blockIdx.x; row < a.batch; row += gridDim.x) {
     __syncthreads();
-    for (int i = tid; i < m; i += 256) bm.set(i, mont_mul<F>(ld_fe(a.ys + 2ull * (row * m + i)), r2));
+    for (int i = tid; i < m; i += kWbThreads) bm.set(i, mont_mul<F>(ld_fe(a.ys + 2ull * (row * m + i)), r2));
     int result = 1;  // "found no divisors!" unless some e works
     int out_len = 0;
     for (int e = a.e_max; e >= 1; e--) {
       const int ncols = 2 * e + k + 2, rhs = ncols - 1, nvars = ncols - 1;
       __syncthreads();
       // ---- build the system (reed_solomon_wb.py:92-102)
-      for (int idx = tid; idx < nrows * ncols; idx += 256) {
+      for (int idx = tid; idx < nrows * ncols; idx += kWbThreads) {
         int r = idx / ncols, c = idx - r * ncols;
         Fe v = fe_zero();
         if (r < m) {
@@ -300,14 +302,14 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
         }
         M.set(idx, v);
       }
-      for (int c = tid; c < ncols; c += 256) piv_row[c] = -1;
+      for (int c = tid; c < ncols; c += kWbThreads) piv_row[c] = -1;
       __syncthreads();
       // ---- fraction-free Gauss-Jordan over all columns incl. the constants (rref, :157-197)
       int prow = 0, nfree = 0;
       for (int col = 0; col < ncols && prow < nrows; col++) {
         if (tid == 0) misc[0] = nrows;
         __syncthreads();
-        for (int r = prow + tid; r < nrows; r += 256)
+        for (int r = prow + tid; r < nrows; r += kWbThreads)
           if (!fe_is_zero(M.get(r * ncols + col))) atomicMin(&misc[0], r);
         __syncthreads();
         const int pr = misc[0];
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
           continue;
         }
         if (pr != prow) {
-          for (int c = tid; c < ncols; c += 256) {
+          for (int c = tid; c < ncols; c += kWbThreads) {
             Fe x = M.get(prow * ncols + c), y = M.get(pr * ncols + c);
             M.set(prow * ncols + c, y);
             M.set(pr * ncols + c, x);
@@ -329,9 +331,9 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
           row_pc[prow] = col;
         }
         __syncthreads();
-        for (int r = tid; r < nrows; r += 256) fcol.set(r, M.get(r * ncols + col));
+        for (int r = tid; r < nrows; r += kWbThreads) fcol.set(r, M.get(r * ncols + col));
         // columns that can change: free columns seen so far and everything from col on
-        for (int c = col + tid; c < ncols; c += 256) act[nfree + (c - col)] = c;
+        for (int c = col + tid; c < ncols; c += kWbThreads) act[nfree + (c - col)] = c;
         __syncthreads();
         // every other row q becomes piv*row_q - f_q*row_prow.  Columns that can change:
         // the free columns seen so far, everything from `col` on, and -- for the
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
         // row is zero there).  Earlier pivot columns are zero in both rows.
         const int cnt = nfree + (ncols - col) + 1;
         const Fe piv = fcol.get(prow);
-        for (int idx = tid; idx < nrows * cnt; idx += 256) {
+        for (int idx = tid; idx < nrows * cnt; idx += kWbThreads) {
           int r = idx / cnt, ci = idx - r * cnt;
           if (r == prow) continue;
           Fe f = fcol.get(r);
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
       }
       // syntactic pivot test of is_pivot_column for the free columns: exactly one
       // non-zero entry, equal (after normalisation) to 1
-      for (int c = tid; c < nvars; c += 256) {
+      for (int c = tid; c < nvars; c += kWbThreads) {
         pseudo_row[c] = -1;
         if (piv_row[c] >= 0) continue;
         int hits = 0, at = -1;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(256) wb_kernel(WbArgs a) {
       }
       __syncthreads();
       // value of every variable
-      for (int c = tid; c < nvars; c += 256) {
+      for (int c = tid; c < nvars; c += kWbThreads) {
         int r = piv_row[c] >= 0 ? piv_row[c] : pseudo_row[c];
         if (r < 0) {
           val.set(c, one);  // free variable := 1
