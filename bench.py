@@ -82,21 +82,28 @@ class ClockSampler(threading.Thread):
         }
         while not self.stop_flag.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
-    def result(self):
-        if not self.samples:
+    def result(self, t0=None, t1=None):
+        """median SM clock over the timed window [t0, t1]; if the window is too short
+        for three samples the warm-up samples (same load) are included"""
+        inside = [c for (t, c) in self.samples if t0 is None or t0 <= t <= t1]
+        window = "timed"
+        if len(inside) < 3:
+            inside = [c for (_, c) in self.samples]
+            window = "warmup+timed"
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
-        s = sorted(self.samples)
+        s = sorted(inside)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s), "window": window}
 
 
 def cpu_reference_run(batch, steps, warmup, threads=0):
@@ -287,21 +294,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(local)
+        sampler.start()
         for i in range(args.warmup):
             step(i % sets)
         barrier()
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local)
-        sampler.start()
         launches0 = ctx.launch_count()
         barrier()
+        host_t0 = time.perf_counter()
         t_start.record(stream)
         for i in range(args.steps):
             step((args.warmup + i) % sets, evs[i])
         t_end.record(stream)
         barrier()
+        host_t1 = time.perf_counter()
         launches = ctx.launch_count() - launches0
         sampler.stop_flag.set()
         sampler.join()
@@ -431,7 +440,7 @@ def run_b200(args):
                        "parallelism": f"batch shard x{world}" + (f" + all-gather ({gather_mode})" if world > 1 else ""),
                        "polys_per_s": value / K},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": sampler.result(),
+            "clocks": sampler.result(host_t0, host_t1),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -354,7 +354,7 @@ int launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a) {
 template <class F, int K>
 int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const void* d_in, void* d_out,
                           size_t batch, const GatherDst* gather, size_t gather_row0) {
-  constexpr int T = 128;
+  constexpr int ROWS = 64, SPLIT = K >= 4 ? 2 : 1;
   SmallInterpArgs<K> a;
   a.in = (const uint4*)d_in;
   a.out = (uint4*)d_out;
@@ -366,9 +366,9 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
     memset(&a.gather, 0, sizeof(a.gather));
   }
   memcpy(a.m, m.data(), sizeof(a.m));
-  const size_t in_tile = (size_t)T * K * 32, out_tile = (size_t)T * ((2 * K) | 1) * 16;
+  const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;
   const size_t smem = in_tile > out_tile ? in_tile : out_tile;
-  interp_small_kernel<F, K, T><<<(unsigned)((batch + T - 1) / T), T, smem, ctx->stream>>>(a);
+  interp_small_kernel<F, K, ROWS, SPLIT><<<(unsigned)((batch + ROWS - 1) / ROWS), ROWS * SPLIT, smem, ctx->stream>>>(a);
   return HBG_OK;
 }
 
@@ -397,7 +397,7 @@ int launch_interp(hbg_ctx* ctx, const std::string& key, const void* d_m, int k, 
   bool small = k <= 8 && it != ctx->host_cache.end() && (ctx->matvec_path == 0 || ctx->matvec_path == 3);
   if (!small) return launch_matvec(ctx, d_m, k, k, d_in, k, d_out, k, batch);
   if (batch == 0) return HBG_OK;
-  if ((batch + 127) / 128 > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large");
+  if ((batch + 63) / 64 > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large");
   int rc = bind_field(ctx);
   if (rc) return rc;
   rc = ctx->is_bls ? launch_interp_small_f<FieldBLS>(ctx, k, it->second, d_in, d_out, batch)

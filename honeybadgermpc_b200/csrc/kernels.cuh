@@ -350,37 +350,48 @@ struct SmallInterpArgs {
   uint32_t m[K][K][8];             // M[i][j], Montgomery form
 };
 
-template <class F, int K, int THREADS>
-__global__ void __launch_bounds__(THREADS) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
+// ROWS rows per CTA, SPLIT warps share a row (warp w handles the outputs
+// i = w % SPLIT, w % SPLIT + SPLIT, ...: no divergence inside a warp); the small
+// batch of the headline config is only ~14 warps per SM at one thread per row, so
+// SPLIT = 2 doubles the warps available to hide the IMAD dependency latency.
+template <class F, int K, int ROWS, int SPLIT>
+__global__ void __launch_bounds__(ROWS * SPLIT) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
+  constexpr int THREADS = ROWS * SPLIT;
   extern __shared__ uint4 smem[];
   __shared__ alignas(8) uint64_t bar;
-  const unsigned long long row0 = (unsigned long long)blockIdx.x * THREADS;
+  const unsigned long long row0 = (unsigned long long)blockIdx.x * ROWS;
   unsigned long long left = a.batch - row0;
-  const int rows_here = left < (unsigned long long)THREADS ? (int)left : THREADS;
+  const int rows_here = left < (unsigned long long)ROWS ? (int)left : ROWS;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) tma_load_1d(smem, a.in + 2ull * row0 * K, (unsigned)rows_here * K * 32u, &bar);
   mbar_wait(&bar, 0);
-  const bool active = (int)threadIdx.x < rows_here;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int part = warp % SPLIT;
+  const int row = (warp / SPLIT) * 32 + lane;
+  const bool active = row < rows_here;
   Fe y[K];
 #pragma unroll
-  for (int j = 0; j < K; j++) y[j] = active ? ld_fe(smem + 2 * (threadIdx.x * K + j)) : fe_zero();
+  for (int j = 0; j < K; j++) y[j] = active ? ld_fe(smem + 2 * (row * K + j)) : fe_zero();
   __syncthreads();
   constexpr int pstride = (2 * K) | 1;
-  uint4* mine = smem + threadIdx.x * pstride;
+  uint4* mine = smem + row * pstride;
 #pragma unroll
-  for (int i = 0; i < K; i++) {
-    Acc acc;
-    acc_zero(acc);
+  for (int i0 = 0; i0 < K; i0 += SPLIT) {
+    const int i = i0 + part;
+    if (i < K) {
+      Acc acc;
+      acc_zero(acc);
 #pragma unroll
-    for (int j = 0; j < K; j++) {
-      Fe m;
+      for (int j = 0; j < K; j++) {
+        Fe m;
 #pragma unroll
-      for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
-      acc_mac(acc, y[j], m);
-      if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
+        for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
+        acc_mac(acc, y[j], m);
+        if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
+      }
+      st_fe(mine + 2 * i, acc_redc<F>(acc));
     }
-    st_fe(mine + 2 * i, acc_redc<F>(acc));
   }
   __syncthreads();
   if (a.gather.world > 0)
