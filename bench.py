@@ -219,9 +219,12 @@ def run_b200(args):
                     handles.append(symm_mem.rendezvous(buf, dist.group.WORLD))
                     gathered.append(buf)
                 mc = int(getattr(handles[0], "multicast_ptr", 0) or 0)
-                if args.gather == "p2p":
-                    mc = 0
-                gather_mode = "fused-multimem" if mc else "fused-p2p"
+                if args.gather == "copy":
+                    gather_mode = "multimem-copy" if mc else "p2p-copy"
+                elif args.gather == "auto":
+                    gather_mode = "fused-multimem" if mc else "fused-p2p"
+                else:
+                    gather_mode = "fused-p2p"
             except Exception as exc:  # noqa: BLE001
                 if rank == 0:
                     print(f"[bench] symmetric memory unavailable ({exc!r}); using NCCL all-gather",
@@ -238,20 +241,33 @@ def run_b200(args):
 
     names = {}
 
+    # both kernels of the step run back to back on one compute stream; for N > 1 the
+    # all-gather of the decoded block runs on a side stream (see below)
+    # With <= 4 ranks the fused kernel leaves SM time free while it waits on NVLink, so the
+    # (independent) encode of the step overlaps it on a second stream; at 8 ranks the kernel
+    # is NVLink-ingress bound for its whole duration and co-scheduling only slows both
+    # (measured: 2.18e10 shares/s back to back vs 1.91e10 overlapped), so they run in order.
+    overlap_encode = world > 1 and world <= 4 and gather_mode.startswith("fused")
+    enc_stream = torch.cuda.Stream(device=dev) if overlap_encode else stream
+
     def step(s, evs=None):
+        ctx.set_stream(enc_stream.cuda_stream)
         if evs is not None:
-            evs[0].record(stream)
+            evs[0].record(enc_stream)
         ctx.fft_batch_evaluate(omega, pt.order, c[s].data_ptr(), batch, K, N_PARTIES,
                                e[s].data_ptr(), _native.MEM_DEVICE)
         if "encode" not in names:
             names["encode"] = ctx.last_kernel()
         if evs is not None:
-            evs[1].record(stream)
+            evs[1].record(enc_stream)
+        ctx.set_stream(stream.cuda_stream)
+        fused = handles and gather_mode.startswith("fused")
         if handles:
             slot = s % len(gathered)
             h = handles[slot]
             if slot_done[slot] is not None:
                 stream.wait_event(slot_done[slot])  # the previous gather into this slot is complete everywhere
+        if fused:
             use_mc = int(getattr(h, "multicast_ptr", 0) or 0) if gather_mode == "fused-multimem" else 0
             ctx.fft_batch_interpolate_allgather(omega, pt.order, ZS, y[s].data_ptr(), batch,
                                                 list(h.buffer_ptrs), use_mc, rank)
@@ -271,6 +287,15 @@ def run_b200(args):
             written.record(stream)
             with torch.cuda.stream(side):
                 side.wait_event(written)
+                if not fused:
+                    # copy kernel: a few CTAs push this rank's block into every rank's buffer
+                    # (multimem.st -> replicated by the NVSwitch) while `stream` moves on
+                    ctx.set_stream(side.cuda_stream)
+                    ctx.allgather_block(r[s].data_ptr(), batch * K * E, list(handles[slot].buffer_ptrs),
+                                        int(getattr(handles[slot], "multicast_ptr", 0) or 0)
+                                        if gather_mode == "multimem-copy" else 0,
+                                        rank * batch * K * E, args.gather_ctas)
+                    ctx.set_stream(stream.cuda_stream)
                 handles[slot].barrier()
                 slot_done[slot] = torch.cuda.Event()
                 slot_done[slot].record(side)
@@ -299,7 +324,7 @@ def run_b200(args):
         for i in range(args.warmup):
             step(i % sets)
         barrier()
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
         launches0 = ctx.launch_count()
@@ -308,6 +333,7 @@ def run_b200(args):
         t_start.record(stream)
         for i in range(args.steps):
             step((args.warmup + i) % sets, evs[i])
+        stream.wait_stream(enc_stream)
         t_end.record(stream)
         barrier()
         host_t1 = time.perf_counter()
@@ -327,7 +353,7 @@ def run_b200(args):
     if handles:
         last = (args.warmup + args.steps - 1) % sets
         g = gathered[last % len(gathered)]
-        assert torch.equal(g[rank * batch:(rank + 1) * batch], c[last]), "fused gather: own block mismatch"
+        assert torch.equal(g[rank * batch:(rank + 1) * batch], c[last]), "gather: own block mismatch"
         sums = g.view(world, -1).sum(dim=1)
         lo, hi = sums.clone(), sums.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
@@ -437,7 +463,10 @@ def run_b200(args):
                        "field": "BLS12-381 r", "z": ZS,
                        "l2": f"{sets} rotating buffer sets of {(enc_bytes + dec_bytes) / 1e6:.0f} MB "
                              "(inputs+outputs larger than the 126 MB L2)",
-                       "parallelism": f"batch shard x{world}" + (f" + all-gather ({gather_mode})" if world > 1 else ""),
+                       "parallelism": f"batch shard x{world}" + (
+                           f" + all-gather ({gather_mode})"
+                           + (", encode overlapped on a second stream" if overlap_encode else "")
+                           if world > 1 else ""),
                        "polys_per_s": value / K},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.result(host_t0, host_t1),
@@ -458,9 +487,12 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--sets", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="N>1: fused stores into symmetric memory (multicast if available), "
-                         "peer stores only, or an overlapped NCCL all-gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "copy", "nccl"],
+                    help="N>1: auto = the interpolation kernel stores its block into every rank's "
+                         "symmetric-memory buffer itself (multimem.st when a multicast address exists); "
+                         "p2p = the same with peer stores only; copy = separate side-stream copy kernel; "
+                         "nccl = overlapped NCCL all-gather")
+    ap.add_argument("--gather-ctas", type=int, default=16)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

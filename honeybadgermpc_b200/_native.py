@@ -76,6 +76,10 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
          ctypes.c_int]),
+    "hbg_allgather_block": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_size_t, ctypes.c_int, ctypes.c_int]),
     "hbg_gao_decode_batch": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -215,6 +219,12 @@ class Context:
         self._check(self.lib.hbg_fft_batch_interpolate_allgather(
             self.handle, _ptr(omega), n, _ptr(zs), len(zs), _ptr(ys), batch, arr,
             int(multicast_ptr) if multicast_ptr else None, len(peer_ptrs), rank))
+
+    def allgather_block(self, block_ptr, nbytes, peer_ptrs, multicast_ptr, offset_bytes, max_ctas=0):
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.hbg_allgather_block(
+            self.handle, int(block_ptr), nbytes, arr, int(multicast_ptr) if multicast_ptr else None,
+            offset_bytes, len(peer_ptrs), max_ctas))
 
     def gao_decode_batch(self, xs, k, ys, batch, coeffs, locator, loc_stride, loc_len, status,
                          mem=MEM_HOST):

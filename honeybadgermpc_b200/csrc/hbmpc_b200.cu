@@ -876,6 +876,32 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
                   });
 }
 
+int hbg_allgather_block(hbg_ctx* ctx, const void* block, size_t bytes, void* const* peer_out,
+                        void* multicast_out, size_t offset_bytes, int world, int max_ctas) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!block || !peer_out || world < 1 || world > 8 || (bytes & 15) || (offset_bytes & 15))
+    return fail(ctx, HBG_ERR_INVALID, "bad argument (sizes and offsets must be multiples of 16)");
+  if (bytes == 0) return HBG_OK;
+  CU(cudaSetDevice(ctx->device));
+  GatherDst g;
+  memset(&g, 0, sizeof(g));
+  g.world = world;
+  g.mc = (uint4*)multicast_out;
+  for (int r = 0; r < world; r++) {
+    if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
+    g.peers[r] = (uint4*)peer_out[r];
+  }
+  unsigned long long chunks = bytes / 16;
+  unsigned long long want = (chunks + 255) / 256;
+  unsigned ctas = (unsigned)(max_ctas > 0 ? max_ctas : 16);
+  if (ctas > want) ctas = (unsigned)want;
+  gather_copy_kernel<<<ctas, 256, 0, ctx->stream>>>((const uint4*)block, g, offset_bytes / 16, chunks);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "gather_copy_kernel";
+  return HBG_OK;
+}
+
 int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], int n, const int32_t* zs,
                                         int k, const uint64_t* ys, size_t batch, void* const* peer_out,
                                         void* multicast_out, int world, int rank) {

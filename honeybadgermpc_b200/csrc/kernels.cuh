@@ -237,6 +237,25 @@ HB_D void tile_store_rows_gather(uint4* tile, const GatherDst& g, unsigned long 
   }
 }
 
+// All-gather of an already decoded block as a copy kernel: a handful of CTAs read
+// the local block and store it into every rank's gather buffer (one multimem.st
+// per 16 bytes when a multicast address is available, so each rank's egress is 1x
+// its block and the NVSwitch does the replication).  Launched on a side stream it
+// overlaps the next step's kernels while occupying only a few SMs.
+__global__ void __launch_bounds__(256) gather_copy_kernel(const uint4* src, GatherDst g,
+                                                          unsigned long long chunk0,
+                                                          unsigned long long chunks) {
+  for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < chunks;
+       q += (unsigned long long)gridDim.x * 256) {
+    uint4 v = src[q];
+    if (g.mc) {
+      st_multimem(g.mc + chunk0 + q, v);
+    } else {
+      for (int w = 0; w < g.world; w++) g.peers[w][chunk0 + q] = v;
+    }
+  }
+}
+
 // within the 8-point transform: after s stages slot idx depends on the inputs
 // j = idx (mod 8 >> s); with the first D8 inputs non-zero it is non-zero iff that
 // residue is < D8

@@ -135,6 +135,15 @@ int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], i
                                         void* const* peer_out, void* multicast_out,
                                         int world, int rank);
 
+/* The all-gather alone: copy an already decoded block (device memory) to byte
+ * offset offset_bytes of every rank's gather buffer -- multimem.st through the
+ * NVSwitch multicast address when multicast_out is non-NULL, peer stores
+ * otherwise -- with at most max_ctas CTAs (0 = 16), so that on a side stream it
+ * overlaps the next batch's kernels.  Enqueued on the context's stream. */
+int hbg_allgather_block(hbg_ctx* ctx, const void* block, size_t bytes,
+                        void* const* peer_out, void* multicast_out,
+                        size_t offset_bytes, int world, int max_ctas);
+
 /* gao_interpolate(x, y, k, modulus, ...), pyx:389-439 + gao_interpolate /
  * gao_interpolate_fft / partial_gcd, rsdecode_impl.h:281-405 -- batched: every
  * row of ys is one received word on the SAME m points xs (erasures already
