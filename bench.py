@@ -261,6 +261,8 @@ def run_b200(args):
         if evs is not None:
             evs[1].record(enc_stream)
         ctx.set_stream(stream.cuda_stream)
+        if evs is not None and overlap_encode:
+            evs[3].record(stream)
         fused = handles and gather_mode.startswith("fused")
         if handles:
             slot = s % len(gathered)
@@ -346,7 +348,7 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / args.steps
-    dec_ms = sum(ev[1].elapsed_time(ev[2]) for ev in evs) / args.steps
+    dec_ms = sum(ev[3 if overlap_encode else 1].elapsed_time(ev[2]) for ev in evs) / args.steps
 
     # parity inside the bench: every decoded block equals its coefficients
     used = min(sets, args.warmup + args.steps)
