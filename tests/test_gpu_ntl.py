@@ -215,3 +215,25 @@ def test_fused_allgather_world1(ntl):
     ctx.fft_batch_interpolate_allgather(omega, pt.order, zs, ys.data_ptr(), batch, [out.data_ptr()], 0, 0)
     ctx.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint64), c)
+
+
+def test_config5_shard_round_trip(ntl):
+    """BASELINE config 5 (n=128, t=42) on one shard-sized batch: NTT-128 encode,
+    interpolate from 43 scattered points, all kernels' variants agree."""
+    n, k, batch = 128, 43, 8192
+    pt = orc.EvalPoint(P, n, True)
+    rng = np.random.default_rng(0xB205)
+    c = rng.integers(0, 2 ** 62, size=(batch, k, 4), dtype=np.uint64)
+    omega = ntl.pack_vec([pt.omega], P)[0]
+    enc = ntl.fft_batch_evaluate_limbs(c, omega, P, pt.order, n)
+    zs = sorted(random.Random(5).sample(range(n), k))
+    ys = np.ascontiguousarray(enc[:, zs, :])
+    for path in ("auto", "global", "smem"):
+        ntl._ctx(P).set_matvec_path(path)
+        assert np.array_equal(ntl.fft_batch_interpolate_limbs(zs, ys, omega, P, pt.order), c), path
+    ntl._ctx(P).set_matvec_path("auto")
+    rows = [0, 17, batch - 1]
+    assert ntl.unpack_rows(enc[rows]) == orc.fft_batch_evaluate(ntl.unpack_rows(c[rows]), pt.omega, P, pt.order, n)
+    ntl._ctx(P).set_fft_path("matrix")
+    assert np.array_equal(ntl.fft_batch_evaluate_limbs(c[:512], omega, P, pt.order, n), enc[:512])
+    ntl._ctx(P).set_fft_path("auto")

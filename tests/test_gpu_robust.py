@@ -216,3 +216,32 @@ def test_wb_config3_shape(rs):
         want.append((c, bad))
     assert wb.robust_decode_batch(list(range(n)), rows) == want
     assert gao.robust_decode_batch(list(range(n)), rows) == want
+
+
+def test_config3_batch_property(rs):
+    """BASELINE config 3 shape at a reduced batch (2048 words, n=64, t=21, exactly 21
+    corrupted evaluations each): size-independent property on the limb boundary --
+    both decoders return the message, and WB's result does not depend on the batch
+    split."""
+    from honeybadgermpc_b200 import ntl, robust
+
+    n, t, batch = 64, 21, 2048
+    k = t + 1
+    xs = ntl.pack_vec(list(range(1, n + 1)), P)
+    rng = np.random.default_rng(0xB203)
+    msg = rng.integers(0, 2 ** 62, size=(batch, k, 4), dtype=np.uint64)
+    enc = ntl.vandermonde_batch_evaluate_limbs(xs, msg, P)
+    noise = rng.integers(0, 2 ** 62, size=(batch, n, 4), dtype=np.uint64)
+    bad = np.zeros((batch, n), dtype=bool)
+    for b in range(batch):
+        bad[b, rng.choice(n, t, replace=False)] = True
+    words = np.where(bad[:, :, None], noise, enc)
+    coeffs, out_len, status = robust.wb_decode_batch_limbs(xs, words, k, (n - t) // 2, P)
+    assert (status == 0).all() and np.array_equal(coeffs, msg)
+    c2, _, s2 = robust.wb_decode_batch_limbs(xs, words[:100], k, (n - t) // 2, P)
+    assert (s2 == 0).all() and np.array_equal(c2, msg[:100])
+    gc, loc, ll, gst = robust.gao_decode_batch_limbs(xs, words, k, P)
+    assert (gst == 0).all() and np.array_equal(gc, msg) and (ll == t + 1).all()
+    # the locator vanishes exactly on the corrupted positions
+    ev = ntl.vandermonde_batch_evaluate_limbs(xs, loc, P)
+    assert np.array_equal(~ev.any(axis=2), bad)
