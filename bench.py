@@ -450,9 +450,9 @@ def run_b200(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             sample = 16384
-            v, dt, cores = cpu_reference_run(sample, 12, 1)
+            v, dt, cores = cpu_reference_run(sample, 40, 1)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{sample} polynomials x 12 steps of the same encode+interpolate; "
+                   "sample": f"{sample} polynomials x 40 steps of the same encode+interpolate; "
                              "oracle/cpu_ref.cpp (C++ restatement of rsdecode_impl.h, OpenMP over the batch)",
                    "ms_per_step": dt * 1e3}
         line = {

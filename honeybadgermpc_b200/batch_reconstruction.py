@@ -65,9 +65,16 @@ def recv_each_party(recv, n):
 
 
 async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=None,
-                            use_omega_powers=False, debug=False, degree=None):
+                            use_omega_powers=False, debug=False, degree=None, wire="ints"):
     """Open ``len(secret_shares)`` shared values; returns them as ``GFElement``
-    (or ``None`` when a round cannot be decoded)."""
+    (or ``None`` when a round cannot be decoded).
+
+    ``wire="ints"`` (default) sends the reference's message format -- lists of
+    Python ints -- and interoperates with reference parties.  ``wire="limbs"``
+    sends every R1/R2 payload as ``bytes`` of 32-byte little-endian limbs (the
+    encoder's output column as is): no int <-> limb
+    marshalling on the steady-state path, 32 B per element on the wire instead
+    of a pickled int list.  All parties of a run must use the same format."""
     bench = logging.LoggerAdapter(logging.getLogger("benchmark_logger"), {"node_id": myid})
     if degree is None:
         degree = t
@@ -101,8 +108,15 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     chunks = chunk_data(shares, degree + 1)
     num_chunks = len(chunks)
     t0 = time.time()
-    for dest, column in enumerate(transpose_lists(enc.encode(chunks))):
-        send(dest, ("R1", column))
+    if wire == "limbs":
+        from .ntl import pack_rows
+
+        encoded = enc.encode_batch_limbs(pack_rows(chunks, degree + 1, p))  # [chunks][n][4]
+        for dest in range(n):
+            send(dest, ("R1", encoded[:, dest, :].tobytes()))
+    else:
+        for dest, column in enumerate(transpose_lists(enc.encode(chunks))):
+            send(dest, ("R1", column))
     bench.info(f"[BatchReconstruct] P1 Send: {time.time() - t0}")
 
     t0 = time.time()
@@ -118,7 +132,12 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
 
     # round 2: broadcast the constant terms (= the chunk polynomials at my point)
     t0 = time.time()
-    message = [row[0] for row in round1]
+    if wire == "limbs":
+        from .ntl import pack_rows
+
+        message = pack_rows([[row[0] for row in round1]], num_chunks, p)[0].tobytes()
+    else:
+        message = [row[0] for row in round1]
     for dest in range(n):
         send(dest, ("R2", message))
     bench.info(f"[BatchReconstruct] P2 Send: {time.time() - t0}")

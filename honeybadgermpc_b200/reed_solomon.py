@@ -36,6 +36,17 @@ class DecodeValidationError(HoneyBadgerMPCError):
     pass
 
 
+def _canonical(col, p):
+    """every row of uint64[rows, 4] is < p"""
+    pl = [(p >> (64 * i)) & (2 ** 64 - 1) for i in range(4)]
+    lt = np.zeros(col.shape[0], dtype=bool)
+    eq = np.ones(col.shape[0], dtype=bool)
+    for i in (3, 2, 1, 0):
+        lt |= eq & (col[:, i] < np.uint64(pl[i]))
+        eq &= col[:, i] == np.uint64(pl[i])
+    return bool(lt.all())
+
+
 def _is_batch(data):
     return type(data[0]) in (list, tuple)
 
@@ -252,6 +263,7 @@ class IncrementalDecoder:
         self._guess = None      # uint64[batch, degree+1, 4]
         self._guess_encoded = None  # uint64[batch, n, 4]
         self._done_rows = []    # rows finished by the robust path (lists of ints)
+        self._result_is_guess = False
         self._result = None
 
     # -- helpers ------------------------------------------------------------
@@ -264,6 +276,27 @@ class IncrementalDecoder:
         if self.validator is not None:
             for v in data:
                 self.validator(v)
+
+    def _to_column(self, data):
+        """list of ints (the reference's wire format) or a packed column
+        (``bytes`` of batch*32 little-endian bytes / ``uint64[batch, 4]``, the
+        limb wire format of ``batch_reconstruct(..., wire="limbs")``)"""
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            col = np.frombuffer(data, dtype=np.uint64).reshape(-1, 4)
+        elif isinstance(data, np.ndarray):
+            col = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
+        else:
+            self._check_input(data)
+            return pack_rows([data], self.batch_size, self.modulus)[0] if self.batch_size else \
+                np.zeros((0, 4), np.uint64)
+        if col.shape[0] != self.batch_size:
+            raise DecodeValidationError("Incorrect length of data")
+        if not _canonical(col, self.modulus):  # a faulty sender: reduce like to_ZZ_p would
+            col = pack_rows(unpack_rows(col[None]), self.batch_size, self.modulus)[0]
+        if self.validator is not None:
+            for v in unpack_rows(col[None])[0]:
+                self.validator(v)
+        return col
 
     def _try_guess(self, idx, col):
         """optimistic path; True while the guess is still standing"""
@@ -278,6 +311,7 @@ class IncrementalDecoder:
             return False
         if len(self._z) >= self._need():
             self._result = unpack_rows(self._guess)
+            self._result_is_guess = True
         return True
 
     def _robust_rounds(self):
@@ -309,9 +343,7 @@ class IncrementalDecoder:
     def add(self, idx, data):
         if self.done() or idx in self._points_seen or idx in self._confirmed_errors:
             return
-        self._check_input(data)
-        col = pack_rows([data], self.batch_size, self.modulus)[0] if self.batch_size else \
-            np.zeros((0, 4), np.uint64)
+        col = self._to_column(data)
         self._points_seen.add(idx)
         self._z.append(idx)
         self._cols.append(col)
@@ -329,6 +361,14 @@ class IncrementalDecoder:
         if self._result is None:
             return None, None
         return self._result, self._confirmed_errors
+
+    def get_results_limbs(self):
+        """the decoded rows as ``uint64[batch, degree+1, 4]`` (no Python ints)"""
+        if self._result is None:
+            return None, None
+        if self._guess is not None and self._result_is_guess:
+            return self._guess, self._confirmed_errors
+        return pack_rows(self._result, self.degree + 1, self.modulus), self._confirmed_errors
 
 
 class EncoderSelector:

@@ -172,7 +172,7 @@ def test_incremental_decoder(rs, omega, algo):
 # --- batch_reconstruct (tests/test_batch_reconstruction.py:12-170) -------------
 
 
-async def _reconstruct(n, t, shares, omega, skip=(), zero=(), delay=0.0, config=None):
+async def _reconstruct(n, t, shares, omega, skip=(), zero=(), delay=0.0, config=None, wire="ints"):
     from honeybadgermpc_b200.batch_reconstruction import batch_reconstruct
     from honeybadgermpc_b200.field import GF
 
@@ -184,7 +184,7 @@ async def _reconstruct(n, t, shares, omega, skip=(), zero=(), delay=0.0, config=
             continue
         ss = [fp(0) for _ in shares[i]] if i in zero else [fp(v) for v in shares[i]]
         jobs.append(batch_reconstruct(ss, P, t, n, i, net.sends[i], net.recvs[i],
-                                      use_omega_powers=omega, config=config))
+                                      use_omega_powers=omega, config=config, wire=wire))
     return await asyncio.gather(*jobs)
 
 
@@ -193,9 +193,10 @@ def test_batch_reconstruct_kats():
 
     shares = [(3, 7, 4), (4, 10, 6), (5, 13, 8), (6, 16, 10)]  # x+2, 3x+4, 2x+2
     for zero in ((), (1,)):
-        for r in run(_reconstruct(4, 1, shares, False, zero=zero, delay=0.01)):
-            assert all(type(e) is GFElement for e in r)
-            assert r == [2, 4, 2]
+        for wire in ("ints", "limbs"):
+            for r in run(_reconstruct(4, 1, shares, False, zero=zero, delay=0.01, wire=wire)):
+                assert all(type(e) is GFElement for e in r)
+                assert r == [2, 4, 2]
     w = _point(4, True).omega.value
     oshares = [((pow(w, i, P) + 2) % P, (3 * pow(w, i, P) + 4) % P) for i in range(4)]
     for zero in ((), (1,)):
@@ -221,9 +222,10 @@ def test_batch_reconstruct_random(n, t, count, omega, algo):
 
     nbad = t if algo == "gao" else 1  # WB raises beyond capacity, see test_incremental_decoder
     for zero in ((), tuple(rng.sample(range(n), nbad))):
-        results = run(_reconstruct(n, t, shares, omega, zero=zero, delay=0.002, config=Cfg))
-        for r in results:
-            assert [e.value for e in r] == secrets
+        for wire in ("ints", "limbs"):
+            results = run(_reconstruct(n, t, shares, omega, zero=zero, delay=0.002, config=Cfg, wire=wire))
+            for r in results:
+                assert [e.value for e in r] == secrets
 
 
 def test_randousha_refinement_algebra(rs):
