@@ -51,6 +51,7 @@ SIGNATURES = {
     "hbg_ctx_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "hbg_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "hbg_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "hbg_ctx_set_host_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_ctx_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "hbg_ctx_last_kernel": (ctypes.c_char_p, [ctypes.c_void_p]),
     "hbg_ctx_set_fft_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -177,6 +178,9 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.hbg_ctx_synchronize(self.handle))
+
+    def set_host_async(self, on):
+        self._check(self.lib.hbg_ctx_set_host_async(self.handle, 1 if on else 0))
 
     def launch_count(self):
         return int(self.lib.hbg_ctx_launch_count(self.handle))

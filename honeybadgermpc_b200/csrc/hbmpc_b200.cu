@@ -49,8 +49,16 @@ struct hbg_ctx {
   uint64_t launches = 0;
   const char* last_kernel = "";
   DevBuf in, out, work, work2;
-  cudaStream_t s_in = nullptr, s_out = nullptr;  // host-buffer pipeline: H2D / D2H streams
-  cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
+  // host-buffer pipeline: H2D / D2H streams and a ring of staging slots, so that with
+  // hbg_ctx_set_host_async consecutive calls overlap (call i+1's H2D under call i's D2H)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  struct HostSlot {
+    DevBuf in, out;
+    cudaEvent_t done = nullptr, ev_in[8] = {}, ev_k[8] = {};
+    bool used = false;
+  } slots[4];
+  unsigned next_slot = 0;
+  bool host_async = false;
   int sm_count = 148;
   std::unordered_map<std::string, DevConst> cache;
   std::unordered_map<std::string, std::vector<uint32_t>> host_cache;  // small tables passed by value
@@ -180,39 +188,38 @@ int run_rows(hbg_ctx* ctx, const void* in, size_t in_row, void* out, size_t out_
              int mem, Launch launch) {
   if (mem == HBG_MEM_DEVICE) return launch(in, out, batch);
   if (mem != HBG_MEM_HOST) return fail(ctx, HBG_ERR_INVALID, "mem must be HBG_MEM_HOST or HBG_MEM_DEVICE");
-  int rc = ensure(ctx, ctx->in, batch * in_row);
-  if (rc) return rc;
-  rc = ensure(ctx, ctx->out, batch * out_row);
-  if (rc) return rc;
-  size_t chunks = batch * (in_row + out_row) >= ((size_t)4 << 20) ? 8 : 1;
-  if (chunks > batch) chunks = 1;
-  if (chunks == 1) {
-    if (in_row) CU(cudaMemcpyAsync(ctx->in.p, in, batch * in_row, cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch(ctx->in.p, ctx->out.p, batch);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(out, ctx->out.p, batch * out_row, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return HBG_OK;
-  }
   if (!ctx->s_in) {
     CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; i++) {
-      CU(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    for (auto& sl : ctx->slots) {
+      CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+      for (int i = 0; i < 8; i++) {
+        CU(cudaEventCreateWithFlags(&sl.ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.ev_k[i], cudaEventDisableTiming));
+      }
     }
   }
+  hbg_ctx::HostSlot& sl = ctx->slots[ctx->next_slot++ % 4];
+  if (sl.used) CU(cudaEventSynchronize(sl.done));  // the slot's previous call has fully drained
+  sl.used = false;
+  int rc = ensure(ctx, sl.in, batch * in_row);
+  if (rc) return rc;
+  rc = ensure(ctx, sl.out, batch * out_row);
+  if (rc) return rc;
+  size_t chunks = batch * (in_row + out_row) >= ((size_t)4 << 20) ? 8 : 1;
+  if (chunks > batch) chunks = 1;
   const size_t per = (batch + chunks - 1) / chunks;
   for (size_t i = 0; i < chunks; i++) {
     const size_t r0 = i * per;
     if (r0 >= batch) break;
     const size_t rows = batch - r0 < per ? batch - r0 : per;
-    uint8_t* d_in = (uint8_t*)ctx->in.p + r0 * in_row;
-    uint8_t* d_out = (uint8_t*)ctx->out.p + r0 * out_row;
-    CU(cudaMemcpyAsync(d_in, (const uint8_t*)in + r0 * in_row, rows * in_row, cudaMemcpyHostToDevice,
-                       ctx->s_in));
-    CU(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+    uint8_t* d_in = (uint8_t*)sl.in.p + r0 * in_row;
+    uint8_t* d_out = (uint8_t*)sl.out.p + r0 * out_row;
+    if (in_row)
+      CU(cudaMemcpyAsync(d_in, (const uint8_t*)in + r0 * in_row, rows * in_row, cudaMemcpyHostToDevice,
+                         ctx->s_in));
+    CU(cudaEventRecord(sl.ev_in[i], ctx->s_in));
+    CU(cudaStreamWaitEvent(ctx->stream, sl.ev_in[i], 0));
     rc = launch(d_in, d_out, rows);
     if (rc) {
       cudaStreamSynchronize(ctx->s_in);
@@ -220,21 +227,29 @@ int run_rows(hbg_ctx* ctx, const void* in, size_t in_row, void* out, size_t out_
       cudaStreamSynchronize(ctx->s_out);
       return rc;
     }
-    CU(cudaEventRecord(ctx->ev_k[i], ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[i], 0));
+    CU(cudaEventRecord(sl.ev_k[i], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->s_out, sl.ev_k[i], 0));
     CU(cudaMemcpyAsync((uint8_t*)out + r0 * out_row, d_out, rows * out_row, cudaMemcpyDeviceToHost,
                        ctx->s_out));
   }
-  CU(cudaStreamSynchronize(ctx->s_out));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaEventRecord(sl.done, ctx->s_out));
+  sl.used = true;
+  if (!ctx->host_async) {
+    CU(cudaEventSynchronize(sl.done));
+    sl.used = false;
+  }
   return HBG_OK;
 }
 
 const size_t kMaxSmem = 226 * 1024;  // 227 KB opt-in limit minus room for static shared memory
 
+// opt in to > 48 KB of dynamic shared memory, once per kernel and device
 template <class K>
 int allow_big_smem(hbg_ctx* ctx, K kernel) {
+  static bool done[64] = {};
+  if (done[ctx->device]) return HBG_OK;
   CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  done[ctx->device] = true;
   return HBG_OK;
 }
 
@@ -785,11 +800,18 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->work.p) cudaFree(ctx->work.p);
   if (ctx->work2.p) cudaFree(ctx->work2.p);
   if (ctx->s_in) {
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->s_out);
     cudaStreamDestroy(ctx->s_in);
     cudaStreamDestroy(ctx->s_out);
-    for (int i = 0; i < 8; i++) {
-      cudaEventDestroy(ctx->ev_in[i]);
-      cudaEventDestroy(ctx->ev_k[i]);
+    for (auto& sl : ctx->slots) {
+      if (sl.in.p) cudaFree(sl.in.p);
+      if (sl.out.p) cudaFree(sl.out.p);
+      if (sl.done) cudaEventDestroy(sl.done);
+      for (int i = 0; i < 8; i++) {
+        if (sl.ev_in[i]) cudaEventDestroy(sl.ev_in[i]);
+        if (sl.ev_k[i]) cudaEventDestroy(sl.ev_k[i]);
+      }
     }
   }
   cudaStreamDestroy(ctx->own_stream);
@@ -808,6 +830,21 @@ int hbg_ctx_set_stream(hbg_ctx* ctx, void* cuda_stream) {
 int hbg_ctx_synchronize(hbg_ctx* ctx) {
   if (!ctx) return HBG_ERR_INVALID;
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->s_out) {
+    CU(cudaStreamSynchronize(ctx->s_in));
+    CU(cudaStreamSynchronize(ctx->s_out));
+    for (auto& sl : ctx->slots) sl.used = false;
+  }
+  return HBG_OK;
+}
+
+int hbg_ctx_set_host_async(hbg_ctx* ctx, int on) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!on && ctx->host_async) {
+    int rc = hbg_ctx_synchronize(ctx);
+    if (rc) return rc;
+  }
+  ctx->host_async = on != 0;
   return HBG_OK;
 }
 

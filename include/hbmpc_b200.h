@@ -65,6 +65,14 @@ const char* hbg_ctx_last_error(const hbg_ctx* ctx);
  * NULL restores the context's own stream. */
 int hbg_ctx_set_stream(hbg_ctx* ctx, void* cuda_stream);
 int hbg_ctx_synchronize(hbg_ctx* ctx);
+/* HBG_MEM_HOST calls normally return when the result is in the caller's buffer.
+ * With host_async on, the four row-wise batch calls (vandermonde / fft evaluate
+ * and interpolate) only ENQUEUE their copies and kernels (a ring of 4 staging
+ * slots) and return; the caller keeps its host buffers alive and unmodified and
+ * reads results after hbg_ctx_synchronize.  Consecutive calls then overlap on
+ * the PCIe link (H2D of one under D2H of the previous).  Host buffers should be
+ * pinned for the copies to be asynchronous. */
+int hbg_ctx_set_host_async(hbg_ctx* ctx, int on);
 /* Number of kernels this context has launched so far. */
 uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx);
 /* Name of the dominant kernel of the last batch call (for bench.py / profiles). */

@@ -237,3 +237,25 @@ def test_config5_shard_round_trip(ntl):
     ntl._ctx(P).set_fft_path("matrix")
     assert np.array_equal(ntl.fft_batch_evaluate_limbs(c[:512], omega, P, pt.order, n), enc[:512])
     ntl._ctx(P).set_fft_path("auto")
+
+
+def test_host_async_mode(ntl):
+    """hbg_ctx_set_host_async: calls only enqueue; results are valid after synchronize;
+    more calls in flight than staging slots still complete in order."""
+    n, k, batch = 16, 6, 40000  # > 4 MB per call: the chunked pipeline
+    pt = orc.EvalPoint(P, n, True)
+    omega = ntl.pack_vec([pt.omega], P)[0]
+    rng = np.random.default_rng(11)
+    ctx = ntl._ctx(P)
+    cs = [rng.integers(0, 2 ** 62, size=(batch, k, 4), dtype=np.uint64) for _ in range(6)]
+    want = [ntl.fft_batch_evaluate_limbs(c, omega, P, pt.order, n) for c in cs]
+    outs = [np.zeros((batch, n, 4), dtype=np.uint64) for _ in cs]
+    ctx.set_host_async(True)
+    try:
+        for c, o in zip(cs, outs):
+            ctx.fft_batch_evaluate(omega, pt.order, c, batch, k, n, o)
+        ctx.synchronize()
+    finally:
+        ctx.set_host_async(False)
+    for o, w in zip(outs, want):
+        assert np.array_equal(o, w)
