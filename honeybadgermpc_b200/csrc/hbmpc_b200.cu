@@ -244,12 +244,16 @@ int run_rows(hbg_ctx* ctx, const void* in, size_t in_row, void* out, size_t out_
 const size_t kMaxSmem = 226 * 1024;  // 227 KB opt-in limit minus room for static shared memory
 
 // opt in to > 48 KB of dynamic shared memory, once per kernel and device
+std::mutex g_smem_mutex;
+std::unordered_map<const void*, uint64_t> g_smem_done;  // kernel -> bit mask of devices
+
 template <class K>
 int allow_big_smem(hbg_ctx* ctx, K kernel) {
-  static bool done[64] = {};
-  if (done[ctx->device]) return HBG_OK;
+  std::lock_guard<std::mutex> lk(g_smem_mutex);
+  uint64_t& mask = g_smem_done[(const void*)kernel];
+  if (mask >> ctx->device & 1) return HBG_OK;
   CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  done[ctx->device] = true;
+  mask |= 1ull << ctx->device;
   return HBG_OK;
 }
 
