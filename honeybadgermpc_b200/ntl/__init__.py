@@ -64,9 +64,7 @@ def _el_bytes(v, p):
     return v.to_bytes(32, "little")  # OverflowError for negatives, as in the reference
 
 
-def pack_rows(rows, width, p):
-    """list of (ragged) int rows -> uint64[len(rows), width, 4]; short rows are
-    zero padded, long rows truncated."""
+def _pack_rows_py(rows, width, p):
     parts = []
     for row in rows:
         m = len(row)
@@ -79,13 +77,10 @@ def pack_rows(rows, width, p):
     return np.frombuffer(buf, dtype=np.uint64).reshape(len(rows), width, 4)
 
 
-def pack_vec(values, p):
-    return pack_rows([values], len(values), p)[0]
-
-
-def unpack_rows(arr):
-    """uint64[batch, width, 4] -> list of lists of int."""
+def _unpack_rows_py(arr):
     batch, width = arr.shape[0], arr.shape[1]
+    if batch * width == 0:
+        return [[] for _ in range(batch)]
     mv = memoryview(np.ascontiguousarray(arr)).cast("B")
     frm = int.from_bytes
     out = []
@@ -95,6 +90,55 @@ def unpack_rows(arr):
         pos += 32 * width
         out.append(row)
     return out
+
+
+def _load_marshal():
+    """The C helper (csrc/pymarshal.c, built by __graft_entry__.build()); it only
+    converts ints <-> limbs, so a missing helper means the slower pure-Python
+    conversion, not a different result."""
+    import ctypes
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "libhbmpc_pymarshal.so")
+    if not os.path.exists(path) or os.environ.get("HBMPC_B200_PY_MARSHAL"):
+        return None
+    try:
+        lib = ctypes.PyDLL(path)
+        lib.hbg_py_pack_rows.restype = ctypes.py_object
+        lib.hbg_py_pack_rows.argtypes = [ctypes.py_object, ctypes.c_ssize_t, ctypes.py_object,
+                                         ctypes.c_void_p]
+        lib.hbg_py_unpack_rows.restype = ctypes.py_object
+        lib.hbg_py_unpack_rows.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_ssize_t]
+        return lib
+    except (OSError, AttributeError):
+        return None
+
+
+_marshal = _load_marshal()
+
+
+def pack_rows(rows, width, p):
+    """list of (ragged) int rows -> uint64[len(rows), width, 4]; short rows are
+    zero padded, long rows truncated; values are reduced mod p (intToZZp,
+    pyx:31-32); negative ints raise OverflowError as in the reference."""
+    if _marshal is None:
+        return _pack_rows_py(rows, width, p)
+    out = np.empty((len(rows), width, 4), dtype=np.uint64)
+    _marshal.hbg_py_pack_rows(rows, width, p, out.ctypes.data)
+    return out
+
+
+def pack_vec(values, p):
+    return pack_rows([values], len(values), p)[0]
+
+
+def unpack_rows(arr):
+    """uint64[batch, width, 4] -> list of lists of int."""
+    if _marshal is None:
+        return _unpack_rows_py(arr)
+    arr = np.ascontiguousarray(arr)
+    return _marshal.hbg_py_unpack_rows(arr.ctypes.data, arr.shape[0], arr.shape[1])
 
 
 def _strip(a):

@@ -17,7 +17,7 @@
 // itself pinned by the reference's KATs and golden fixtures) in
 // tests/test_cpu_ref.py.
 //
-// Build: g++ -O3 -march=native -fopenmp -shared -fPIC cpu_ref.cpp
+// Build: g++ -O3 -march=x86-64-v3 -fopenmp -shared -fPIC cpu_ref.cpp  (__graft_entry__.build_oracle)
 #include <omp.h>
 #include <stdint.h>
 #include <string.h>

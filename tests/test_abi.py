@@ -73,6 +73,33 @@ def test_product_never_imports_oracle():
                 assert "cpu_ref" not in text and "hbmpc_oracle" not in text, f
 
 
+def test_c_marshalling_matches_python():
+    """csrc/pymarshal.c against the pure-Python conversion, incl. the reference's
+    error behaviour (negative ints -> OverflowError, pyx:20-22)"""
+    import random
+
+    import numpy as np
+
+    graft.build_marshal()
+    import importlib
+
+    import honeybadgermpc_b200.ntl as ntl
+
+    ntl = importlib.reload(ntl)
+    assert ntl._marshal is not None
+    rng = random.Random(5)
+    rows = [[rng.randrange(P) for _ in range(rng.randint(0, 7))] for _ in range(200)]
+    rows += [[0, 1, P - 1, P, 2 * P + 5, 2 ** 300 + 7], (3, 4, 5), [True]]
+    for width in (0, 1, 4, 7):
+        a = ntl.pack_rows(rows, width, P)
+        assert np.array_equal(a, ntl._pack_rows_py(rows, width, P))
+        assert ntl.unpack_rows(a) == ntl._unpack_rows_py(a)
+    assert ntl.pack_rows([[27, 5]], 2, 13).tolist() == ntl._pack_rows_py([[27, 5]], 2, 13).tolist()
+    for bad, exc in (([[-1]], OverflowError), ([["x"]], TypeError), ([[1.5]], TypeError)):
+        with pytest.raises(exc):
+            ntl.pack_rows(bad, 1, P)
+
+
 def test_host_marshalling_round_trip():
     from honeybadgermpc_b200.ntl import pack_rows, unpack_rows
 
