@@ -9,6 +9,7 @@
 
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -373,7 +374,6 @@ int launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a) {
 template <class F, int K>
 int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const void* d_in, void* d_out,
                           size_t batch, const GatherDst* gather, size_t gather_row0) {
-  constexpr int ROWS = 64, SPLIT = K >= 4 ? 2 : 1;
   SmallInterpArgs<K> a;
   a.in = (const uint4*)d_in;
   a.out = (uint4*)d_out;
@@ -385,9 +385,18 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
     memset(&a.gather, 0, sizeof(a.gather));
   }
   memcpy(a.m, m.data(), sizeof(a.m));
-  const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;
-  const size_t smem = in_tile > out_tile ? in_tile : out_tile;
-  interp_small_kernel<F, K, ROWS, SPLIT><<<(unsigned)((batch + ROWS - 1) / ROWS), ROWS * SPLIT, smem, ctx->stream>>>(a);
+  static int split_env = getenv("HBG_INTERP_SPLIT") ? atoi(getenv("HBG_INTERP_SPLIT")) : 0;
+  auto go = [&](auto rows_c, auto split_c) {
+    constexpr int ROWS = decltype(rows_c)::value, SPLIT = decltype(split_c)::value;
+    const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;
+    interp_small_kernel<F, K, ROWS, SPLIT><<<(unsigned)((batch + ROWS - 1) / ROWS), ROWS * SPLIT,
+                                             in_tile + out_tile, ctx->stream>>>(a);
+  };
+  using std::integral_constant;
+  if (K >= 6 && split_env == 3) go(integral_constant<int, 64>{}, integral_constant<int, 3>{});
+  else if (K >= 6 && split_env == 6) go(integral_constant<int, 32>{}, integral_constant<int, 6>{});
+  else if (K >= 4 && split_env != 1) go(integral_constant<int, 64>{}, integral_constant<int, 2>{});
+  else go(integral_constant<int, 64>{}, integral_constant<int, 1>{});
   return HBG_OK;
 }
 

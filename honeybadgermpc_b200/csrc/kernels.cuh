@@ -389,12 +389,12 @@ __global__ void __launch_bounds__(ROWS * SPLIT) interp_small_kernel(const __grid
   const int part = warp % SPLIT;
   const int row = (warp / SPLIT) * 32 + lane;
   const bool active = row < rows_here;
-  Fe y[K];
-#pragma unroll
-  for (int j = 0; j < K; j++) y[j] = active ? ld_fe(smem + 2 * (row * K + j)) : fe_zero();
-  __syncthreads();
+  // the inputs stay in the shared tile (re-read per term: two LDS.128) instead of in
+  // 8*K registers, which buys resident warps -- the kernel is latency bound
+  const uint4* yrow = smem + 2 * (active ? row : 0) * K;
   constexpr int pstride = (2 * K) | 1;
-  uint4* mine = smem + row * pstride;
+  uint4* otile = smem + 2 * ROWS * K;
+  uint4* mine = otile + row * pstride;
 #pragma unroll
   for (int i0 = 0; i0 < K; i0 += SPLIT) {
     const int i = i0 + part;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(ROWS * SPLIT) interp_small_kernel(const __grid
         Fe m;
 #pragma unroll
         for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
-        acc_mac(acc, y[j], m);
+        acc_mac(acc, ld_fe(yrow + 2 * j), m);
         if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
       }
       st_fe(mine + 2 * i, acc_redc<F>(acc));
@@ -414,9 +414,9 @@ __global__ void __launch_bounds__(ROWS * SPLIT) interp_small_kernel(const __grid
   }
   __syncthreads();
   if (a.gather.world > 0)
-    tile_store_rows_gather<THREADS>(smem, a.gather, 2ull * (a.gather_row0 + row0) * K, rows_here, 2 * K);
+    tile_store_rows_gather<THREADS>(otile, a.gather, 2ull * (a.gather_row0 + row0) * K, rows_here, 2 * K);
   else
-    tile_store_rows<THREADS>(smem, a.out + 2ull * row0 * K, rows_here, 2 * K);
+    tile_store_rows<THREADS>(otile, a.out + 2ull * row0 * K, rows_here, 2 * K);
 }
 
 // ---------------------------------------------------------------------------
