@@ -259,3 +259,58 @@ def test_host_async_mode(ntl):
         ctx.set_host_async(False)
     for o, w in zip(outs, want):
         assert np.array_equal(o, w)
+
+
+def test_c_abi_error_paths(ntl):
+    """the C-ABI returns codes (never throws, never crashes) on bad arguments"""
+    import ctypes
+
+    from honeybadgermpc_b200 import _native
+
+    lib = _native.load_library()
+    ctx = ntl._ctx(P)
+    h = ctx.handle
+    good = ntl.pack_vec([1, 2, 3], P)
+    polys = ntl.pack_rows([[1, 2]], 2, P)
+    out = np.zeros((1, 3, 4), np.uint64)
+    # null pointers / bad sizes / bad mem flag
+    assert lib.hbg_vandermonde_batch_evaluate(h, None, 3, polys.ctypes.data, 1, 2, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    assert lib.hbg_vandermonde_batch_evaluate(h, good.ctypes.data, 3, None, 1, 2, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    assert lib.hbg_vandermonde_batch_evaluate(h, good.ctypes.data, 3, polys.ctypes.data, 1, 2, out.ctypes.data, 7) == _native.HBG_ERR_INVALID
+    assert lib.hbg_vandermonde_batch_evaluate(h, good.ctypes.data, -1, polys.ctypes.data, 1, 2, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    assert b"" != lib.hbg_ctx_last_error(h)
+    # non-canonical evaluation point
+    bad = ntl.pack_vec([1, 2, 3], P).copy()
+    bad[2] = np.frombuffer((P + 1).to_bytes(32, "little"), dtype=np.uint64)
+    assert lib.hbg_vandermonde_batch_evaluate(h, bad.ctypes.data, 3, polys.ctypes.data, 1, 2, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    # repeated points -> singular
+    rep = ntl.pack_vec([5, 5], P)
+    assert lib.hbg_vandermonde_batch_interpolate(h, rep.ctypes.data, 2, polys.ctypes.data, 1, out.ctypes.data, 0) == _native.HBG_ERR_SINGULAR
+    # fft: size not a power of two, omega of the wrong order, k_out > n
+    w4 = ntl.pack_vec([ROOTS_OF_UNITY[2]], P)
+    assert lib.hbg_fft_batch_evaluate(h, w4.ctypes.data, 6, polys.ctypes.data, 1, 2, 3, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    assert lib.hbg_fft_batch_evaluate(h, w4.ctypes.data, 8, polys.ctypes.data, 1, 2, 3, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    assert lib.hbg_fft_batch_evaluate(h, w4.ctypes.data, 4, polys.ctypes.data, 1, 2, 5, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    zs = np.array([0, 0], dtype=np.int32)
+    assert lib.hbg_fft_batch_interpolate(h, w4.ctypes.data, 4, zs.ctypes.data, 2, polys.ctypes.data, 1, out.ctypes.data, 0) == _native.HBG_ERR_SINGULAR
+    zs = np.array([0, 9], dtype=np.int32)
+    assert lib.hbg_fft_batch_interpolate(h, w4.ctypes.data, 4, zs.ctypes.data, 2, polys.ctypes.data, 1, out.ctypes.data, 0) == _native.HBG_ERR_INVALID
+    # contexts: even modulus / too large modulus / bad device
+    hh = ctypes.c_void_p()
+    for mod, want in ((16, _native.HBG_ERR_INVALID), (2 ** 255 + 95, _native.HBG_ERR_UNSUPPORTED)):
+        limbs = np.frombuffer(mod.to_bytes(32, "little"), dtype=np.uint64).copy()
+        assert lib.hbg_ctx_create(ctypes.byref(hh), limbs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 0) == want
+    limbs = np.frombuffer(P.to_bytes(32, "little"), dtype=np.uint64).copy()
+    assert lib.hbg_ctx_create(ctypes.byref(hh), limbs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 99) == _native.HBG_ERR_CUDA
+    # the context still works afterwards
+    assert ntl.vandermonde_batch_evaluate([1, 2, 3], [[1, 2]], P) == [[3, 5, 7]]
+
+
+def test_empty_batches(ntl):
+    z = np.zeros((0, 6, 4), np.uint64)
+    omega = ntl.pack_vec([ROOTS_OF_UNITY[4]], P)[0]
+    assert ntl.fft_batch_evaluate_limbs(z, omega, P, 16, 16).shape == (0, 16, 4)
+    assert ntl.fft_batch_interpolate_limbs([0, 1, 2, 3, 4, 5], z, omega, P, 16).shape == (0, 6, 4)
+    xs = ntl.pack_vec([1, 2, 3, 4, 5, 6], P)
+    assert ntl.vandermonde_batch_evaluate_limbs(xs, z, P).shape == (0, 6, 4)
+    assert ntl.vandermonde_batch_interpolate_limbs(xs, z, P).shape == (0, 6, 4)
