@@ -19,49 +19,72 @@ import logging
 import random
 import time
 
+from . import reed_solomon as rs
 from .field import GF
+from .ntl import pack_rows
 from .polynomial import EvalPoint
-from .reed_solomon import (
-    Algorithm,
-    DecoderFactory,
-    EncoderFactory,
-    IncrementalDecoder,
-    RobustDecoderFactory,
-)
 from .utils import chunk_data, flatten_lists, subscribe_recv, transpose_lists
+
+ROUNDS = ("R1", "R2")
 
 
 async def fetch_one(awaitables):
-    """Yield ``(index, result)`` in completion order (batch_reconstruction.py:25-40)."""
-    index = {aw: i for i, aw in enumerate(awaitables)}
-    pending = set(awaitables)
-    while pending:
-        done, pending = await asyncio.wait(pending, return_when=asyncio.FIRST_COMPLETED)
-        for d in done:
-            yield index[d], await d
+    """Yield ``(index, result)`` as the awaitables complete
+    (batch_reconstruction.py:25-40)."""
+    position = {}
+    for i, aw in enumerate(awaitables):
+        position[aw] = i
+    waiting = set(position)
+    while waiting:
+        finished, waiting = await asyncio.wait(waiting, return_when=asyncio.FIRST_COMPLETED)
+        for task in finished:
+            yield position[task], await task
 
 
 async def incremental_decode(receivers, encoder, decoder, robust_decoder, batch_size, t, degree, n):
-    """batch_reconstruction.py:43-61"""
-    inc = IncrementalDecoder(encoder, decoder, robust_decoder, degree=degree,
-                             batch_size=batch_size, max_errors=t)
-    async for idx, column in fetch_one(receivers):
-        inc.add(idx, column)
-        if inc.done():
-            return inc.get_results()[0]
+    """Feed columns to an ``IncrementalDecoder`` in arrival order until it is
+    done (batch_reconstruction.py:43-61); ``None`` if the senders run out."""
+    state = rs.IncrementalDecoder(encoder, decoder, robust_decoder, degree=degree,
+                                  batch_size=batch_size, max_errors=t)
+    async for sender, column in fetch_one(receivers):
+        state.add(sender, column)
+        if state.done():
+            rows, _ = state.get_results()
+            return rows
     return None
 
 
 def recv_each_party(recv, n):
-    """One queue per sender (batch_reconstruction.py:64-85)."""
-    queues = [asyncio.Queue() for _ in range(n)]
+    """Split one ``recv() -> (sender, payload)`` stream into a getter per sender
+    (batch_reconstruction.py:64-85).  Returns ``(pump task, [getter] * n)``."""
+    boxes = [asyncio.Queue() for _ in range(n)]
 
     async def pump():
         while True:
             sender, payload = await recv()
-            queues[sender].put_nowait(payload)
+            boxes[sender].put_nowait(payload)
 
-    return asyncio.create_task(pump()), [q.get for q in queues]
+    return asyncio.create_task(pump()), [box.get for box in boxes]
+
+
+class _Inbox:
+    """All receive plumbing of one reconstruction: tag demultiplexer, then one
+    pending ``get`` per (round, sender)."""
+
+    def __init__(self, recv, n):
+        self.tasks = []
+        demux_task, subscribe = subscribe_recv(recv)
+        self.tasks.append(demux_task)
+        self.columns = {}
+        for tag in ROUNDS:
+            pump_task, getters = recv_each_party(subscribe(tag), n)
+            self.tasks.append(pump_task)
+            self.columns[tag] = [asyncio.create_task(get()) for get in getters]
+            self.tasks.extend(self.columns[tag])
+
+    def close(self):
+        for task in self.tasks:
+            task.cancel()
 
 
 async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=None,
@@ -75,85 +98,62 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     encoder's output column as is): no int <-> limb
     marshalling on the steady-state path, 32 B per element on the wire instead
     of a pickled int list.  All parties of a run must use the same format."""
-    bench = logging.LoggerAdapter(logging.getLogger("benchmark_logger"), {"node_id": myid})
-    if degree is None:
-        degree = t
-    shares = [v.value for v in secret_shares]
-    if config is not None and config.induce_faults:
+    timing = logging.LoggerAdapter(logging.getLogger("benchmark_logger"), {"node_id": myid})
+    k = (t if degree is None else degree) + 1
+    values = [share.value for share in secret_shares]
+    if config is not None and config.induce_faults:  # fault injection hook of the reference (:129-131)
         logging.debug("[FAULT][BatchReconstruction] Sending random shares.")
-        shares = [random.randint(0, p - 1) for _ in shares]
+        values = [random.randint(0, p - 1) for _ in values]
 
-    subscribe_task, subscribe = subscribe_recv(recv)
-    del recv
-    task_r1, getters_r1 = recv_each_party(subscribe("R1"), n)
-    data_r1 = [asyncio.create_task(g()) for g in getters_r1]
-    task_r2, getters_r2 = recv_each_party(subscribe("R2"), n)
-    data_r2 = [asyncio.create_task(g()) for g in getters_r2]
-    del subscribe
-    background = [task_r1, task_r2, subscribe_task, *data_r1, *data_r2]
+    inbox = _Inbox(recv, n)
+    field = GF(p)
+    point = EvalPoint(field, n, use_omega_powers=use_omega_powers)
+    kind = rs.Algorithm.FFT if use_omega_powers else rs.Algorithm.VANDERMONDE
+    codec = (rs.EncoderFactory.get(point, kind), rs.DecoderFactory.get(point, kind),
+             rs.RobustDecoderFactory.get(
+                 t, point, algorithm=rs.Algorithm.GAO if config is None else config.decoding_algorithm))
+    chunks = chunk_data(values, k)
 
-    def cancel_all():
-        for task in background:
-            task.cancel()
+    async def decode_round(tag):
+        started = time.time()
+        try:
+            rows = await incremental_decode(inbox.columns[tag], *codec, len(chunks), t, k - 1, n)
+        except asyncio.CancelledError:
+            inbox.close()
+            raise
+        if rows is None:
+            logging.error("[BatchReconstruct] %s reconstruction failed!", "P1" if tag == "R1" else "P2")
+        else:
+            timing.info("[BatchReconstruct] %s Reconstruct: %s", "P1" if tag == "R1" else "P2",
+                        time.time() - started)
+        return rows
 
-    fp = GF(p)
-    point = EvalPoint(fp, n, use_omega_powers=use_omega_powers)
-    algo = Algorithm.FFT if use_omega_powers else Algorithm.VANDERMONDE
-    enc = EncoderFactory.get(point, algo)
-    dec = DecoderFactory.get(point, algo)
-    robust_dec = RobustDecoderFactory.get(
-        t, point, algorithm=Algorithm.GAO if config is None else config.decoding_algorithm)
-
-    # round 1: every party gets one evaluation of each chunk polynomial
-    chunks = chunk_data(shares, degree + 1)
-    num_chunks = len(chunks)
-    t0 = time.time()
+    # R1: party j receives the j-th evaluation of every chunk polynomial
+    started = time.time()
     if wire == "limbs":
-        from .ntl import pack_rows
-
-        encoded = enc.encode_batch_limbs(pack_rows(chunks, degree + 1, p))  # [chunks][n][4]
-        for dest in range(n):
-            send(dest, ("R1", encoded[:, dest, :].tobytes()))
+        encoded = codec[0].encode_batch_limbs(pack_rows(chunks, k, p))  # [chunks][n][4]
+        outgoing = [encoded[:, j, :].tobytes() for j in range(n)]
     else:
-        for dest, column in enumerate(transpose_lists(enc.encode(chunks))):
-            send(dest, ("R1", column))
-    bench.info(f"[BatchReconstruct] P1 Send: {time.time() - t0}")
-
-    t0 = time.time()
-    try:
-        round1 = await incremental_decode(data_r1, enc, dec, robust_dec, num_chunks, t, degree, n)
-    except asyncio.CancelledError:
-        cancel_all()
-        raise
-    if round1 is None:
-        logging.error("[BatchReconstruct] P1 reconstruction failed!")
+        outgoing = transpose_lists(codec[0].encode(chunks))
+    for j, column in enumerate(outgoing):
+        send(j, ("R1", column))
+    timing.info("[BatchReconstruct] P1 Send: %s", time.time() - started)
+    mine = await decode_round("R1")
+    if mine is None:
         return None
-    bench.info(f"[BatchReconstruct] P1 Reconstruct: {time.time() - t0}")
 
-    # round 2: broadcast the constant terms (= the chunk polynomials at my point)
-    t0 = time.time()
-    if wire == "limbs":
-        from .ntl import pack_rows
-
-        message = pack_rows([[row[0] for row in round1]], num_chunks, p)[0].tobytes()
-    else:
-        message = [row[0] for row in round1]
-    for dest in range(n):
-        send(dest, ("R2", message))
-    bench.info(f"[BatchReconstruct] P2 Send: {time.time() - t0}")
-
-    t0 = time.time()
-    try:
-        round2 = await incremental_decode(data_r2, enc, dec, robust_dec, num_chunks, t, degree, n)
-    except asyncio.CancelledError:
-        cancel_all()
-        raise
-    if round2 is None:
-        logging.error("[BatchReconstruct] P2 reconstruction failed!")
+    # R2: broadcast the constant terms = the chunk polynomials G_c at my point
+    started = time.time()
+    constants = [row[0] for row in mine]
+    payload = pack_rows([constants], len(chunks), p)[0].tobytes() if wire == "limbs" else constants
+    for j in range(n):
+        send(j, ("R2", payload))
+    timing.info("[BatchReconstruct] P2 Send: %s", time.time() - started)
+    secrets = await decode_round("R2")
+    if secrets is None:
         return None
-    bench.info(f"[BatchReconstruct] P2 Reconstruct: {time.time() - t0}")
 
-    cancel_all()
-    opened = flatten_lists(round2)
-    assert len(opened) >= len(shares)
-    return [fp(v) for v in opened[: len(shares)]]
+    inbox.close()
+    opened = flatten_lists(secrets)
+    assert len(opened) >= len(values)
+    return [field(v) for v in opened[: len(values)]]

@@ -244,3 +244,30 @@ def test_randousha_refinement_algebra(rs):
     polys = [[rng.randrange(P) for _ in range(t + 1)] + [0] * (n - t - 1) for _ in range(rows)]
     shares = enc.encode(polys)
     assert dec.decode(list(range(n)), shares) == polys
+
+
+@pytest.mark.parametrize("omega", [False, True])
+def test_robust_reconstruct_single_share(rs, omega):
+    """robust_reconstruction.py:14-30 -- one shared value, one faulty party"""
+    from honeybadgermpc_b200.field import GF
+    from honeybadgermpc_b200.robust_reconstruction import robust_reconstruct
+
+    n, t = 7, 2
+    fp = GF(P)
+    pt = _point(n, omega)
+    rng = random.Random(3)
+    coeffs = [rng.randrange(P) for _ in range(t + 1)]
+    shares = [orc.poly_eval(coeffs, pt(i).value, P) for i in range(n)]
+    shares[5] = (shares[5] + 1) % P  # party 5 is the second to arrive (delays below)
+
+    async def go():
+        loop = asyncio.get_event_loop()
+        futs = []
+        for i in range(n):
+            f = loop.create_future()
+            loop.call_later(0.001 * ((i * 3) % n), f.set_result, fp(shares[i]))
+            futs.append(f)
+        return await robust_reconstruct(futs, fp, n, t, pt, t)
+
+    poly, errors = run(go())
+    assert poly == coeffs and errors == {5}
