@@ -156,4 +156,4 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     inbox.close()
     opened = flatten_lists(secrets)
     assert len(opened) >= len(values)
-    return [field(v) for v in opened[: len(values)]]
+    return field.wrap_canonical(opened[: len(values)])

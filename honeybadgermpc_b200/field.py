@@ -68,6 +68,24 @@ class GF:
         # same draw as the reference (field.py:64-65) so get_omega(seed=0) agrees
         return GFElement(Random(seed).randint(0, self.modulus - 1), self)
 
+    def wrap_canonical(self, values):
+        """``[GFElement(v, self) for v in values]`` for ints already in [0, p) --
+        what ``batch_reconstruct`` returns.  Skips the per-element ``int() % p``
+        of the constructor: wrapping B results is otherwise the single largest
+        cost of a large open once the kernels are fast."""
+        new = object.__new__
+        cls = GFElement
+        modulus = self.modulus
+        out = []
+        append = out.append
+        for v in values:
+            e = new(cls)
+            e.value = v
+            e.field = self
+            e.modulus = modulus
+            append(e)
+        return out
+
 
 class GFElement:
     __slots__ = ("value", "field", "modulus")
