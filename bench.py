@@ -247,7 +247,13 @@ def run_b200(args):
     # (independent) encode of the step overlaps it on a second stream; at 8 ranks the kernel
     # is NVLink-ingress bound for its whole duration and co-scheduling only slows both
     # (measured: 2.18e10 shares/s back to back vs 1.91e10 overlapped), so they run in order.
-    overlap_encode = world > 1 and world <= 4 and gather_mode.startswith("fused")
+    # N = 1: the encode and the interpolation of a step are independent launches, so they go
+    # to two streams: each kernel fills the GPU in a single wave (1024 CTAs for 1036 slots)
+    # and spends ~8 us of its ~30 us ramping up and draining; on two streams the next
+    # kernel's CTAs take over SM by SM as the previous kernel's CTAs retire.  The per-kernel
+    # durations of the roofline come from a second, serial pass over the same steps.
+    overlap_encode = (world > 1 and world <= 4 and gather_mode.startswith("fused")) or \
+        (world == 1 and not args.serial)
     enc_stream = torch.cuda.Stream(device=dev) if overlap_encode else stream
 
     def step(s, evs=None):
@@ -340,6 +346,17 @@ def run_b200(args):
         barrier()
         host_t1 = time.perf_counter()
         launches = ctx.launch_count() - launches0
+        serial_evs = None
+        if world == 1 and overlap_encode:
+            # serial pass (not part of `value`): the same steps with both kernels on one stream,
+            # so each kernel's CUDA-event duration is its own
+            enc_stream_saved, enc_stream = enc_stream, stream
+            serial_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                          for _ in range(min(args.steps, 200))]
+            for i, ev in enumerate(serial_evs):
+                step((args.warmup + i) % sets, ev)
+            barrier()
+            enc_stream = enc_stream_saved
         sampler.stop_flag.set()
         sampler.join()
     total_ms = t_start.elapsed_time(t_end)
@@ -349,6 +366,11 @@ def run_b200(args):
         total_ms = float(tt.item())
     enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / args.steps
     dec_ms = sum(ev[3 if overlap_encode else 1].elapsed_time(ev[2]) for ev in evs) / args.steps
+    overlapped_ms = None
+    if serial_evs is not None:
+        overlapped_ms = {"encode": enc_ms, "interpolate": dec_ms}
+        enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in serial_evs) / len(serial_evs)
+        dec_ms = sum(ev[1].elapsed_time(ev[2]) for ev in serial_evs) / len(serial_evs)
 
     # parity inside the bench: every decoded block equals its coefficients
     used = min(sets, args.warmup + args.steps)
@@ -403,6 +425,9 @@ def run_b200(args):
                 "frac": achieved / peak, "traffic": traffic, "kernel": f"{dom}: {names[dom]}",
                 "peak_source": peak_src,
                 "kernel_ms": {"encode": enc_ms, "interpolate": dec_ms}, "kernels": names,
+                "kernel_ms_source": ("serial pass after the timed region (the timed steps overlap the two "
+                                     "kernels on two streams)" if serial_evs is not None else "timed region"),
+                "kernel_ms_overlapped": overlapped_ms,
                 "step_GBps": (enc_bytes + dec_bytes) / (ms_per_step * 1e-3) / 1e9,
                 "int_pipe": {"achieved_imad_wide_per_s": imad_rate, "peak_imad_wide_per_s": imad_peak,
                              "frac": imad_rate / imad_peak,
@@ -472,6 +497,8 @@ def run_b200(args):
                        "field": "BLS12-381 r", "z": ZS,
                        "l2": f"{sets} rotating buffer sets of {(enc_bytes + dec_bytes) / 1e6:.0f} MB "
                              "(inputs+outputs larger than the 126 MB L2)",
+                       "streams": ("encode and interpolate of a step on two streams" if overlap_encode
+                                   else "one stream"),
                        "parallelism": f"batch shard x{world}" + (
                            f" + all-gather ({gather_mode})"
                            + (", encode overlapped on a second stream" if overlap_encode else "")
@@ -496,6 +523,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--sets", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--serial", action="store_true",
+                    help="N=1: run the two kernels of a step back to back on one stream")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "copy", "nccl"],
                     help="N>1: auto = the interpolation kernel stores its block into every rank's "
                          "symmetric-memory buffer itself (multimem.st when a multicast address exists); "

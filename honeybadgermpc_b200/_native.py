@@ -189,11 +189,11 @@ class Context:
         return self.lib.hbg_ctx_last_kernel(self.handle).decode()
 
     def set_fft_path(self, path):
-        self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2, "ntt-smem": 3}[path]))
+        self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2, "ntt-smem": 3, "ntt-split": 4}[path]))
 
     def set_matvec_path(self, path):
         self._check(self.lib.hbg_ctx_set_matvec_path(
-            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3}[path]))
+            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3, "small-r29": 4}[path]))
 
     # -- batch operations (limb arrays or device pointers) ------------------
     def vandermonde_batch_evaluate(self, xs, polys, batch, d, out, mem=MEM_HOST):

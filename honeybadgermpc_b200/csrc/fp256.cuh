@@ -39,6 +39,11 @@ struct FieldParams {
   uint32_t one[8];   // R mod p     (Montgomery form of 1)
   uint32_t n0inv;    // -p^{-1} mod 2^32
   uint32_t pad[7];
+  // radix-2^29 view of the same modulus (carry-free lazy dot products, rowmath.cuh)
+  uint32_t p29[9];   // p = sum p29[i] 2^(29 i)
+  uint32_t n0inv29;  // -p^{-1} mod 2^29
+  uint32_t r261[8];  // 2^261 mod p, plain residue: mont_mul(x*R, r261) = x * 2^261 mod p
+  uint32_t pad2[6];
 };
 
 #if defined(__CUDACC__)
@@ -53,6 +58,12 @@ struct FieldBLS {
          : i == 6 ? 0x299d7d48u : 0x73eda753u;
   }
   static HB_HD constexpr uint32_t n0inv() { return 0xffffffffu; }
+  static HB_HD constexpr uint32_t p29(int i) {
+    return i == 0 ? 0x00000001u : i == 1 ? 0x1ffffff8u : i == 2 ? 0x1f96ffbfu
+         : i == 3 ? 0x1b4805ffu : i == 4 ? 0x1d80553bu : i == 5 ? 0x0c0404d0u
+         : i == 6 ? 0x1520cce7u : i == 7 ? 0x0a6533afu : 0x0073eda7u;
+  }
+  static HB_HD constexpr uint32_t n0inv29() { return 0x1fffffffu; }
   // p = 1 (mod 2^32) and p[1] = 2^32-1: the two lowest columns of m*p are
   // adds/subs of m, not multiplies (see redc_row_low_ones).
   static constexpr bool kLowOnes = true;
@@ -68,12 +79,16 @@ struct FieldBLSConst;
 struct FieldAny {
   static HB_D uint32_t p(int i) { return c_field.p[i]; }
   static HB_D uint32_t n0inv() { return c_field.n0inv; }
+  static HB_D uint32_t p29(int i) { return c_field.p29[i]; }
+  static HB_D uint32_t n0inv29() { return c_field.n0inv29; }
   static constexpr bool kLowOnes = false;
   static constexpr int kFold = 1;
 };
 struct FieldBLSConst {
   static HB_D uint32_t p(int i) { return c_field.p[i]; }
   static HB_D uint32_t n0inv() { return 0xffffffffu; }
+  static HB_D uint32_t p29(int i) { return c_field.p29[i]; }
+  static HB_D uint32_t n0inv29() { return 0x1fffffffu; }
   static constexpr bool kLowOnes = true;
   static constexpr int kFold = 2;
 };
@@ -88,6 +103,8 @@ struct FieldHost {
   }
   static inline uint32_t p(int i) { return cur()->p[i]; }
   static inline uint32_t n0inv() { return cur()->n0inv; }
+  static inline uint32_t p29(int i) { return cur()->p29[i]; }
+  static inline uint32_t n0inv29() { return cur()->n0inv29; }
   static constexpr bool kLowOnes = false;
   static constexpr int kFold = 1;
 };
@@ -349,8 +366,10 @@ HB_HD Fe fe_zero() {
   return r;
 }
 
-// Montgomery product a*b/R mod p, canonical output.  Requires b < p and
-// a < 2^256 (a need not be reduced), or both < p.
+// Montgomery product a*b/R mod p, canonical output.  a is the multiplicand (all
+// of its limbs enter every row), b supplies the row digits.  Requires a < p; b
+// may be any value < 2^256 (every row keeps t < a + p, the result is < 2p
+// before the final conditional subtraction).
 template <class F>
 HB_HD Fe mont_mul(const Fe& a, const Fe& b) {
   uint32_t x[8], y[8];  // two column accumulators whose even/odd roles swap every row

@@ -44,8 +44,10 @@ struct hbg_ctx {
   FieldParams fp;
   HostField* field = nullptr;
   bool is_bls = false;
-  int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel
-  int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel
+  int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel,
+                        // 4 ntt with the register-resident split kernel for n = 16
+  int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel,
+                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic
   std::string err;
   uint64_t launches = 0;
   const char* last_kernel = "";
@@ -361,8 +363,27 @@ int launch_ntt16_t(hbg_ctx* ctx, const Ntt16Args& a) {
   return HBG_OK;
 }
 
+// d <= 8: two 4-point groups per thread, results stored from registers (no output tile)
+template <class F, int D>
+int launch_ntt16_g4_t(hbg_ctx* ctx, const Ntt16Args& a) {
+  constexpr int POLYS = 64;  // per CTA of 128 threads
+  constexpr bool BAL = false;  // even->odd hand-over (rowmath.cuh: ntt16_offload): measured, not a gain
+  // input tile (+ hand-over slots, 4 elements per polynomial, when balancing)
+  ntt16_g4_kernel<F, D, POLYS, BAL><<<(unsigned)((a.batch + POLYS - 1) / POLYS), 2 * POLYS,
+                                      (size_t)POLYS * a.d * 32 + (BAL ? (size_t)POLYS * 4 * 32 : 0),
+                                      ctx->stream>>>(a);
+  return HBG_OK;
+}
+
 template <class F>
 int launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a) {
+  if (a.d <= 8 && a.stride == a.d && ctx->fft_path != 4) {
+    ctx->last_kernel = "ntt16_g4_kernel";
+    if (a.d <= 4) return launch_ntt16_g4_t<F, 4>(ctx, a);
+    if (a.d <= 6) return launch_ntt16_g4_t<F, 6>(ctx, a);
+    return launch_ntt16_g4_t<F, 8>(ctx, a);
+  }
+  ctx->last_kernel = "ntt16_split_kernel";
   if (a.d <= 4) return launch_ntt16_t<F, 4>(ctx, a);
   if (a.d <= 6) return launch_ntt16_t<F, 6>(ctx, a);
   if (a.d <= 8) return launch_ntt16_t<F, 8>(ctx, a);
@@ -385,18 +406,32 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
     memset(&a.gather, 0, sizeof(a.gather));
   }
   memcpy(a.m, m.data(), sizeof(a.m));
-  static int split_env = getenv("HBG_INTERP_SPLIT") ? atoi(getenv("HBG_INTERP_SPLIT")) : 0;
-  auto go = [&](auto rows_c, auto split_c) {
-    constexpr int ROWS = decltype(rows_c)::value, SPLIT = decltype(split_c)::value;
-    const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;
-    interp_small_kernel<F, K, ROWS, SPLIT><<<(unsigned)((batch + ROWS - 1) / ROWS), ROWS * SPLIT,
-                                             in_tile + out_tile, ctx->stream>>>(a);
-  };
-  using std::integral_constant;
-  if (K >= 6 && split_env == 3) go(integral_constant<int, 64>{}, integral_constant<int, 3>{});
-  else if (K >= 6 && split_env == 6) go(integral_constant<int, 32>{}, integral_constant<int, 6>{});
-  else if (K >= 4 && split_env != 1) go(integral_constant<int, 64>{}, integral_constant<int, 2>{});
-  else go(integral_constant<int, 64>{}, integral_constant<int, 1>{});
+  {  // the same matrix for the radix-2^29 arithmetic: limbs of M[i][j] * 2^261 mod p
+    const HostField& f = *ctx->field;
+    Fe r261;
+    memcpy(r261.w, ctx->fp.r261, 32);
+    for (int e = 0; e < K * K; e++) {
+      Fe v;
+      memcpy(v.w, &m[(size_t)e * 8], 32);
+      to_limbs29(f.mul(v, r261), a.m29[e / K][e % K]);
+    }
+  }
+  const int arith_env = ctx->matvec_path == 4 ? 1 : 0;
+  // two warps share 32 rows for K >= 4 (each thread K/2 outputs), one thread per row below
+  constexpr int ROWS = 64, SPLIT = K >= 4 ? 2 : 1;
+  const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;
+  const unsigned grid = (unsigned)((batch + ROWS - 1) / ROWS);
+  if (gather) {  // fused all-gather: results go through a shared tile to every rank's buffer
+    if (arith_env == 1)
+      interp_small_kernel<F, K, ROWS, SPLIT, true, 1><<<grid, ROWS * SPLIT, in_tile + out_tile, ctx->stream>>>(a);
+    else
+      interp_small_kernel<F, K, ROWS, SPLIT, true, 0><<<grid, ROWS * SPLIT, in_tile + out_tile, ctx->stream>>>(a);
+  } else {       // local output: one 256-bit store per element straight from registers
+    if (arith_env == 1)
+      interp_small_kernel<F, K, ROWS, SPLIT, false, 1><<<grid, ROWS * SPLIT, in_tile, ctx->stream>>>(a);
+    else
+      interp_small_kernel<F, K, ROWS, SPLIT, false, 0><<<grid, ROWS * SPLIT, in_tile, ctx->stream>>>(a);
+  }
   return HBG_OK;
 }
 
@@ -422,7 +457,7 @@ int launch_interp_small_f(hbg_ctx* ctx, int k, const std::vector<uint32_t>& m, c
 int launch_interp(hbg_ctx* ctx, const std::string& key, const void* d_m, int k, const void* d_in,
                   void* d_out, size_t batch) {
   auto it = ctx->host_cache.find(key);
-  bool small = k <= 8 && it != ctx->host_cache.end() && (ctx->matvec_path == 0 || ctx->matvec_path == 3);
+  bool small = k <= 8 && it != ctx->host_cache.end() && (ctx->matvec_path == 0 || ctx->matvec_path >= 3);
   if (!small) return launch_matvec(ctx, d_m, k, k, d_in, k, d_out, k, batch);
   if (batch == 0) return HBG_OK;
   if ((batch + 63) / 64 > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large");
@@ -449,7 +484,13 @@ int launch_ntt(hbg_ctx* ctx, const void* d_tw, const std::vector<uint32_t>* h_tw
     a.d = d < 16 ? d : 16;
     a.stride = d;
     a.k_out = k_out;
-    memcpy(a.tw, h_tw->data(), sizeof(a.tw));
+    memcpy(a.tw, h_tw->data(), 8 * 32);  // omega^0 .. omega^7
+    for (int i = 0; i < 8; i++) {         // omega^(8+i) = -omega^i
+      Fe w;
+      memcpy(w.w, a.tw[i], 32);
+      w = ctx->field->neg(w);
+      memcpy(a.tw[8 + i], w.w, 32);
+    }
     size_t blocks = (batch + 63) / 64;
     if (blocks == 0) return HBG_OK;
     if (blocks > 0x7fffffffull) return fail(ctx, HBG_ERR_UNSUPPORTED, "batch too large for one launch");
@@ -457,7 +498,6 @@ int launch_ntt(hbg_ctx* ctx, const void* d_tw, const std::vector<uint32_t>* h_tw
     if (rc) return rc;
     CU(cudaGetLastError());
     ctx->launches++;
-    ctx->last_kernel = "ntt16_split_kernel";
     return HBG_OK;
   }
   int log_n = ilog2(n);
@@ -865,13 +905,13 @@ uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches :
 const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 3) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 4) return HBG_ERR_INVALID;
   ctx->matvec_path = path;
   return HBG_OK;
 }
 
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 3) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 4) return HBG_ERR_INVALID;
   ctx->fft_path = path;
   return HBG_OK;
 }

@@ -64,8 +64,17 @@ inline bool field_params_init(const uint64_t p64[4], FieldParams* fp) {
     bool take = carry || !borrow;
     for (int j = 0; j < 8; j++) x.w[j] = take ? s[j] : d[j];
     if (i == 255) memcpy(fp->one, x.w, sizeof(x.w));
+    if (i == 260) memcpy(fp->r261, x.w, sizeof(x.w));  // 2^261 mod p, plain residue
   }
   memcpy(fp->r2, x.w, sizeof(x.w));
+  // radix-2^29 view: limbs of p and -p^-1 mod 2^29
+  for (int i = 0; i < 9; i++) {
+    int bit = 29 * i, wd = bit / 32, sh = bit % 32;
+    uint64_t v = p.w[wd] >> sh;
+    if (sh > 3 && wd + 1 < 8) v |= (uint64_t)p.w[wd + 1] << (32 - sh);
+    fp->p29[i] = (uint32_t)v & 0x1fffffffu;
+  }
+  fp->n0inv29 = fp->n0inv & 0x1fffffffu;
   return true;
 }
 

@@ -8,6 +8,7 @@
 // is the plain product, so no conversion pass ever touches the batch.
 #pragma once
 #include "fp256.cuh"
+#include "rowmath.cuh"
 
 namespace hb {
 
@@ -22,6 +23,32 @@ HB_D Fe ld_fe(const uint4* p) {
 HB_D void st_fe(uint4* p, const Fe& r) {
   p[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
   p[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+}
+
+// Shared-memory element load that the compiler may neither hoist nor merge with an
+// earlier load of the same address: lane-per-row kernels RE-READ their inputs from the
+// TMA-staged tile for every use instead of keeping them in registers (8 registers per
+// element), which is what keeps every row-warp of the batch resident at once.
+HB_D Fe lds_fe_reload(const uint4* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  Fe r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
+               : "r"(a));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];"
+               : "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "r"(a));
+  return r;
+}
+
+// One element = one 32-byte sector = ONE 256-bit global store (STG.E.256, sm_100+).
+// Lane-per-row kernels store their results straight from registers with it: every
+// store fills a whole sector, so no shared-memory transpose is needed to keep the
+// DRAM/L2 traffic at the algorithmic bytes.
+HB_D void st_fe_global256(uint4* p, const Fe& r) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]),
+               "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -187,7 +214,7 @@ struct Ntt16Args {
   uint4* out;         // [batch][k_out]
   unsigned long long batch;
   int d, k_out, stride;  // d <= 16 coefficients used, rows are `stride` elements apart
-  uint32_t tw[8][8];      // omega^i, i < 8, Montgomery form
+  uint32_t tw[16][8];     // omega^i, i < 16, Montgomery form
 };
 
 // Row-per-thread kernels keep global traffic coalesced by staging through shared
@@ -353,6 +380,93 @@ __global__ void __launch_bounds__(2 * POLYS) ntt16_split_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------
+// 16-point NTT of d <= 8 coefficients (the headline encode: d = t+1 = 6), the
+// default n = 16 kernel.  Same two-threads-per-polynomial split as
+// ntt16_split_kernel (warp 2w: even outputs, warp 2w+1: odd outputs), but each
+// thread works through its 8-point transform as two 4-point groups
+// (rowmath.cuh: ntt16_half), re-reading the coefficients from the TMA-staged
+// tile instead of holding all eight values: ~2/3 of the registers, so every
+// row-warp of a 65 536-polynomial batch is resident at once.  Results leave
+// straight from registers, one 256-bit store per element (whole 32-byte
+// sectors), so there is no output tile and no barrier after the TMA wait.
+// ---------------------------------------------------------------------------
+// The multiplier is a real function (one copy, ~230 instructions) instead of 15 inlined
+// copies: the straight-line kernel shrinks from 77 KB to 28 KB of code and fits the 32 KB
+// instruction cache -- with everything inlined 28 % of the issue slots were instruction-
+// fetch stalls (profiles/).  The twiddle comes from a 512-byte shared-memory table.
+template <class F>
+__device__ __noinline__ Fe mul_tw_call(const uint4* twp, Fe x) {
+  return mont_mul<F>(ld_fe(twp), x);
+}
+
+// Hand-over slots between the two threads of a polynomial (rowmath.cuh: ntt16_half):
+// element-major, 16-byte halves apart, so lane-per-row accesses are conflict free.  The
+// two warps of a pair meet on a named barrier (id 1 + pair): the even warp only arrives,
+// the odd warp waits -- long after the even warp has passed.
+template <int POLYS>
+struct Ntt16Xch {
+  uint4* base;   // [4][2][POLYS] uint4
+  int poly, bar_id;
+  HB_D void put(int i, const Fe& v) {
+    base[(2 * i) * POLYS + poly] = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+    base[(2 * i + 1) * POLYS + poly] = make_uint4(v.w[4], v.w[5], v.w[6], v.w[7]);
+  }
+  HB_D Fe get(int i) const {
+    const uint4 lo = base[(2 * i) * POLYS + poly], hi = base[(2 * i + 1) * POLYS + poly];
+    Fe r;
+    r.w[0] = lo.x; r.w[1] = lo.y; r.w[2] = lo.z; r.w[3] = lo.w;
+    r.w[4] = hi.x; r.w[5] = hi.y; r.w[6] = hi.z; r.w[7] = hi.w;
+    return r;
+  }
+  HB_D void signal() {
+    __threadfence_block();
+    asm volatile("barrier.cta.arrive %0, 64;" ::"r"(bar_id) : "memory");
+  }
+  HB_D void wait() { asm volatile("barrier.cta.sync %0, 64;" ::"r"(bar_id) : "memory"); }
+};
+
+template <class F, int D, int POLYS, bool BAL = false>
+__global__ void __launch_bounds__(2 * POLYS, (D <= 6 ? 7 : 5))
+ntt16_g4_kernel(const __grid_constant__ Ntt16Args a) {
+  extern __shared__ uint4 smem[];   // input tile [POLYS][d], then the hand-over slots
+  __shared__ alignas(8) uint64_t bar;
+  __shared__ uint4 twsm[32];  // omega^j, j < 16 (Montgomery form), two 16-byte halves each
+  const unsigned long long row0 = (unsigned long long)blockIdx.x * POLYS;
+  unsigned long long left = a.batch - row0;
+  const int rows_here = left < (unsigned long long)POLYS ? (int)left : POLYS;
+  // rows are dense here (stride == d: the launcher sends everything else to the split kernel)
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (threadIdx.x < 32) {
+    const int j = threadIdx.x >> 1, h = 4 * (threadIdx.x & 1);
+    twsm[threadIdx.x] = make_uint4(a.tw[j][h], a.tw[j][h + 1], a.tw[j][h + 2], a.tw[j][h + 3]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    tma_load_1d(smem, a.in + 2ull * row0 * a.d, (unsigned)rows_here * a.d * 32u, &bar);
+  mbar_wait(&bar, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp & 1;                  // 0: even outputs, 1: odd outputs
+  const int poly = (warp >> 1) * 32 + lane;   // row within the CTA
+  // rows past the end of the batch run on row 0's data and store nothing (with BAL both
+  // warps of a pair must reach the hand-over barrier)
+  const bool active = poly < rows_here;
+  if (!BAL && !active) return;
+  const int d = a.d, k_out = a.k_out;
+  const uint4* src = smem + 2 * (active ? poly : 0) * d;
+  uint4* dst = a.out + 2ull * (row0 + poly) * k_out;
+  Ntt16Xch<POLYS> xch{smem + 2 * POLYS * d, poly, 1 + (warp >> 1)};
+  auto ld = [&](int i) { return i < d ? ld_fe(src + 2 * i) : fe_zero(); };
+  auto mul = [&](int j, const Fe& x) { return mul_tw_call<F>(twsm + 2 * j, x); };  // omega^j * x
+  auto st = [&](int k, const Fe& v) {
+    if (active && k < k_out) st_fe_global256(dst + 2 * k, v);
+  };
+  if (half)
+    ntt16_half<F, D, 1, BAL>(ld, mul, st, xch);
+  else
+    ntt16_half<F, D, 0, BAL>(ld, mul, st, xch);
+}
+
+// ---------------------------------------------------------------------------
 // Small square interpolation (k <= 8), one row per thread: the k x k matrix
 // V(x)^-1 sits in the kernel-parameter constant bank, so its limbs are direct
 // IMAD.WIDE operands (no loads, no registers); the k inputs of the row stay in
@@ -366,15 +480,23 @@ struct SmallInterpArgs {
   unsigned long long batch;
   unsigned long long gather_row0;  // first row of this rank inside the gathered array
   GatherDst gather;                // world == 0: plain local output
-  uint32_t m[K][K][8];             // M[i][j], Montgomery form
+  uint32_t m[K][K][8];             // M[i][j], Montgomery form (R = 2^256): ARITH 0
+  uint32_t m29[K][K][9];           // M[i][j] * 2^261 mod p as 9 x 29-bit limbs: ARITH 1
 };
 
 // ROWS rows per CTA, SPLIT warps share a row (warp w handles the outputs
 // i = w % SPLIT, w % SPLIT + SPLIT, ...: no divergence inside a warp); the small
 // batch of the headline config is only ~14 warps per SM at one thread per row, so
 // SPLIT = 2 doubles the warps available to hide the IMAD dependency latency.
-template <class F, int K, int ROWS, int SPLIT>
-__global__ void __launch_bounds__(ROWS * SPLIT) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
+// GATHER = false: every result leaves straight from registers as one 256-bit
+// store (a whole 32-byte sector).  GATHER = true (fused all-gather): results are
+// parked in a shared tile and streamed to every rank with consecutive 16-byte
+// multimem / peer stores, which keeps the NVLink packets large.
+// ARITH = 1 (default): carry-free radix-2^29 accumulation (rowmath.cuh: mac29 / redc29),
+// plain IMAD.WIDE at twice the issue rate of the carry-chained form.  ARITH = 0: the
+// 32-bit-limb lazy accumulator of fp256.cuh (Acc), kept as a bit-identical second path.
+template <class F, int K, int ROWS, int SPLIT, bool GATHER, int ARITH>
+__global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
   constexpr int THREADS = ROWS * SPLIT;
   extern __shared__ uint4 smem[];
   __shared__ alignas(8) uint64_t bar;
@@ -389,34 +511,57 @@ __global__ void __launch_bounds__(ROWS * SPLIT) interp_small_kernel(const __grid
   const int part = warp % SPLIT;
   const int row = (warp / SPLIT) * 32 + lane;
   const bool active = row < rows_here;
+  if (!GATHER && !active) return;  // no barrier follows on this path
   // the inputs stay in the shared tile (re-read per term: two LDS.128) instead of in
   // 8*K registers, which buys resident warps -- the kernel is latency bound
   const uint4* yrow = smem + 2 * (active ? row : 0) * K;
   constexpr int pstride = (2 * K) | 1;
   uint4* otile = smem + 2 * ROWS * K;
   uint4* mine = otile + row * pstride;
-#pragma unroll
+  uint4* grow = a.out + 2ull * (row0 + row) * K;
+  // not unrolled: one output's accumulator live at a time (72 registers), a third of the code
+#pragma unroll 1
   for (int i0 = 0; i0 < K; i0 += SPLIT) {
     const int i = i0 + part;
     if (i < K) {
-      Acc acc;
-      acc_zero(acc);
+      Fe r;
+      if (ARITH == 1) {
+        uint64_t col[17];
 #pragma unroll
-      for (int j = 0; j < K; j++) {
-        Fe m;
+        for (int c = 0; c < 17; c++) col[c] = 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
-        acc_mac(acc, ld_fe(yrow + 2 * j), m);
-        if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
+        for (int j = 0; j < K; j++) {
+          uint32_t y[9], m[9];
+          to_limbs29(lds_fe_reload(yrow + 2 * j), y);
+#pragma unroll
+          for (int q = 0; q < 9; q++) m[q] = a.m29[i][j][q];
+          mac29(col, y, m);
+        }
+        if (K > 6) norm29(col);  // 7 or 8 terms: make room for the reduction products
+        r = redc29<F>(col);
+      } else {
+        Acc acc;
+        acc_zero(acc);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          Fe m;
+#pragma unroll
+          for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
+          acc_mac(acc, lds_fe_reload(yrow + 2 * j), m);
+          if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
+        }
+        r = acc_redc<F>(acc);
       }
-      st_fe(mine + 2 * i, acc_redc<F>(acc));
+      if (GATHER)
+        st_fe(mine + 2 * i, r);
+      else
+        st_fe_global256(grow + 2 * i, r);
     }
   }
-  __syncthreads();
-  if (a.gather.world > 0)
+  if (GATHER) {
+    __syncthreads();
     tile_store_rows_gather<THREADS>(otile, a.gather, 2ull * (a.gather_row0 + row0) * K, rows_here, 2 * K);
-  else
-    tile_store_rows<THREADS>(otile, a.out + 2ull * row0 * K, rows_here, 2 * K);
+  }
 }
 
 // ---------------------------------------------------------------------------

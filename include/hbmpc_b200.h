@@ -82,13 +82,16 @@ const char* hbg_ctx_last_kernel(const hbg_ctx* ctx);
  * a 16-point Vandermonde base case inside the recursion, rsdecode_impl.h:16,
  * :133-136).  Results are bit-identical.  0 = pick the cheaper (default),
  * 1 = dot products, 2 = butterflies, 3 = butterflies through the generic
- * shared-memory kernel even where a register-resident kernel exists (n = 16). */
+ * shared-memory kernel even where a register-resident kernel exists (n = 16),
+ * 4 = butterflies, n = 16 through the 8-values-in-registers split kernel even
+ * where the 4-point-group kernel (d <= 8, the default) applies. */
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path);
 /* Which dot-product kernel applies a matrix to the batch (results are
  * bit-identical): 0 = pick by size (default), 1 = matrix read through L1 from
  * global memory, 2 = matrix and TMA-staged input tile in shared memory,
  * 3 = k <= 8 interpolation with the matrix in the constant bank, one row per
- * thread (falls back to 0 where it does not apply). */
+ * thread (falls back to 0 where it does not apply), 4 = the same kernel with the
+ * carry-free radix-2^29 accumulator instead of the 32-bit-limb carry chains. */
 int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path);
 
 /* vandermonde_batch_evaluate(x, polynomials, modulus), pyx:199-244 +

@@ -65,7 +65,7 @@ def test_errors(ntl):
 
 
 def test_golden(ntl, golden):
-    for path in ("auto", "matrix", "ntt", "ntt-smem"):
+    for path in ("auto", "matrix", "ntt", "ntt-smem", "ntt-split"):
         ntl._ctx(P).set_fft_path(path)
         kats.check_golden(ntl, golden)
     ntl._ctx(P).set_fft_path("auto")
@@ -90,7 +90,7 @@ def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
     polys = [[rng.randrange(p) for _ in range(rng.randint(1, d))] for _ in range(batch)]
     polys[0] = polys[0] + [p - 1] * (d - len(polys[0]))
     want = orc.vandermonde_batch_evaluate(xs, polys, p)
-    for path in ("auto", "global", "smem", "small"):
+    for path in ("auto", "global", "smem", "small", "small-r29"):
         ntl._ctx(p).set_matvec_path(path)
         assert ntl.vandermonde_batch_evaluate(xs, polys, p) == want, path
     if p > n:
@@ -98,7 +98,7 @@ def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
         xk = rng.sample(xs, k)
         ys = [[rng.randrange(p) for _ in range(k)] for _ in range(batch)]
         want = orc.vandermonde_batch_interpolate(xk, ys, p)
-        for path in ("auto", "global", "smem", "small"):
+        for path in ("auto", "global", "smem", "small", "small-r29"):
             ntl._ctx(p).set_matvec_path(path)
             assert ntl.vandermonde_batch_interpolate(xk, ys, p) == want, path
     ntl._ctx(p).set_matvec_path("auto")
@@ -115,7 +115,8 @@ def test_worst_case_values(ntl):
 
 @pytest.mark.parametrize("r,d,k,batch", [(1, 2, 2, 3), (2, 3, 4, 70), (4, 6, 16, 300), (4, 16, 11, 65),
                                          (4, 1, 16, 9), (4, 4, 16, 130), (4, 5, 7, 129), (4, 8, 16, 31),
-                                         (4, 9, 16, 33), (4, 11, 1, 5), (4, 12, 16, 200), (4, 20, 16, 77),
+                                         (4, 9, 16, 33), (4, 11, 1, 5), (4, 2, 16, 64), (4, 3, 5, 63),
+                                         (4, 7, 16, 129), (4, 6, 6, 1), (4, 8, 3, 200), (4, 5, 16, 1000), (4, 12, 16, 200), (4, 20, 16, 77),
                                          (5, 20, 25, 64), (7, 43, 128, 21), (8, 100, 256, 5),
                                          (10, 700, 1024, 3), (11, 1500, 2048, 2), (12, 4096, 100, 1)])
 def test_fft_vs_oracle(ntl, r, d, k, batch):
@@ -124,7 +125,7 @@ def test_fft_vs_oracle(ntl, r, d, k, batch):
     omega = ROOTS_OF_UNITY[r] if r < len(ROOTS_OF_UNITY) else pow(7, (P - 1) // n, P)
     polys = [[rng.randrange(P) for _ in range(d)] for _ in range(batch)]
     want = orc.fft_batch_evaluate(polys, omega, P, n, k)
-    for path in ("matrix", "ntt", "ntt-smem"):
+    for path in ("matrix", "ntt", "ntt-smem", "ntt-split"):
         if path == "matrix" and k * min(d, n) > 2 ** 18:
             continue
         ntl._ctx(P).set_fft_path(path)
@@ -144,6 +145,15 @@ def test_fft_small_prime(ntl):
     for path in ("matrix", "ntt"):
         ntl._ctx(257).set_fft_path(path)
         assert ntl.fft(c, 3, 257, 256) == orc.fft(c, 3, 257, 256)
+    # n = 16 over small generic fields (FieldAny instantiations of the two n = 16 kernels)
+    for p, w in ((17, 3), (97, 8), (2 ** 64 - 2 ** 32 + 1, pow(7, (2 ** 64 - 2 ** 32) // 16, 2 ** 64 - 2 ** 32 + 1))):
+        for d in (1, 4, 5, 6, 8, 13):
+            polys = [[rng.randrange(p) for _ in range(d)] for _ in range(70)] + [[p - 1] * d]
+            want = orc.fft_batch_evaluate(polys, w, p, 16, 16)
+            for path in ("ntt", "ntt-split", "ntt-smem", "matrix"):
+                ntl._ctx(p).set_fft_path(path)
+                assert ntl.fft_batch_evaluate(polys, w, p, 16, 16) == want, (p, d, path)
+            ntl._ctx(p).set_fft_path("auto")
     with pytest.raises(ValueError):
         ntl.fft([1, 2], 4, 13, 4)  # 4 is not a primitive 4th root mod 13
 
@@ -228,7 +238,7 @@ def test_config5_shard_round_trip(ntl):
     enc = ntl.fft_batch_evaluate_limbs(c, omega, P, pt.order, n)
     zs = sorted(random.Random(5).sample(range(n), k))
     ys = np.ascontiguousarray(enc[:, zs, :])
-    for path in ("auto", "global", "smem"):
+    for path in ("auto", "global", "smem", "small-r29"):
         ntl._ctx(P).set_matvec_path(path)
         assert np.array_equal(ntl.fft_batch_interpolate_limbs(zs, ys, omega, P, pt.order), c), path
     ntl._ctx(P).set_matvec_path("auto")

@@ -109,6 +109,51 @@ def test_pow_inv(lib):
             assert val(pw) == pow(a, e, p) and val(inv) == pow(a, -1, p)
 
 
+@pytest.mark.parametrize("p,omega", [(P, None), (17, 3), (97, 8), (2 ** 64 - 2 ** 32 + 1, None)])
+def test_ntt16_row_math(lib, p, omega):
+    # ntt16_half (the row math of ntt16_g4_kernel) against the DFT definition
+    if omega is None:
+        g = next(g for g in range(2, 50) if pow(g, (p - 1) // 2, p) != 1)
+        omega = pow(g, (p - 1) // 16, p)
+    assert pow(omega, 8, p) == p - 1
+    rng = random.Random(16)
+    out = np.zeros(64, np.uint64)
+    for d in range(0, 9):
+        for mode in ("rand", "max", "one"):
+            c = [rng.randrange(p) if mode == "rand" else (p - 1 if mode == "max" else 1) for _ in range(d)]
+            want = [sum(c[i] * pow(omega, i * k, p) for i in range(d)) % p for k in range(16)]
+            for lowones in ((0, 1) if p == P else (0,)):
+                for bal in (0, 1):  # with / without the even thread's hand-over to the odd thread
+                    out[:] = 0xDEAD
+                    rc = lib.hbt_ntt16(ptr(limbs(p)), d, ptr(many(c)), ptr(limbs(omega)), lowones, bal, ptr(out))
+                    assert rc == 0
+                    got = [val(out[4 * k: 4 * k + 4]) for k in range(16)]
+                    assert got == want, (d, mode, lowones, bal)
+
+
+@pytest.mark.parametrize("p", [P, 13, 53, 2 ** 61 - 1, 2 ** 127 - 1, 2 ** 255 - 19])
+def test_lazy_dot_radix29(lib, p):
+    # to_limbs29 / mac29 / norm29 / redc29 (the row math of interp_small_kernel)
+    rng = random.Random(29)
+    out = np.zeros(4, np.uint64)
+    for n in range(0, 9):
+        for mode in ("rand", "max", "mixed"):
+            if mode == "rand":
+                a = [rng.randrange(p) for _ in range(n)]
+                b = [rng.randrange(p) for _ in range(n)]
+            elif mode == "max":
+                a, b = [p - 1] * n, [p - 1] * n
+            else:
+                a = [rng.choice([0, 1, p - 1, 2 ** 29 - 1, 2 ** 232 % p]) for _ in range(n)]
+                b = [rng.choice([0, 1, p - 1, (p - 1) // 2]) for _ in range(n)]
+            want = sum(x * y for x, y in zip(a, b)) % p
+            for lowones in ((0, 1) if p == P else (0,)):
+                for prenorm in ((0, 1) if n <= 6 else (1,)):
+                    rc = lib.hbt_dot29(ptr(limbs(p)), n, ptr(many(a)), ptr(many(b)), lowones, prenorm, ptr(out))
+                    assert rc == 0
+                    assert val(out) == want, (n, mode, lowones, prenorm)
+
+
 def test_bad_modulus(lib):
     out = np.zeros(4, np.uint64)
     assert lib.hbt_mulmod(ptr(limbs(16)), ptr(limbs(1)), ptr(limbs(1)), ptr(out)) == 1
