@@ -164,6 +164,30 @@ HB_HD void cmad4_top(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a1, uin
 #endif
 }
 
+// Same chain, for the deferred-carry counters of the lazy accumulator (acc_mac): the
+// carry-out is first materialised in a fresh register and then added to the counter.
+// With "addc top, top, 0" ptxas postpones the counter updates (nothing needs them before
+// acc_fold), runs out of predicate registers for the pending carries and packs them bit
+// by bit into a general register: ~250 LOP3 per 6-term dot product, a fifth of the
+// kernel's instructions.  The fresh register ends the predicate's life at once.
+HB_HD void cmad4_cnt(uint32_t* acc, uint32_t& cnt, uint32_t a0, uint32_t a1, uint32_t a2,
+                     uint32_t a3, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t cy;
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+        "+r"(acc[6]), "+r"(acc[7]), "=r"(cy)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+  cnt += cy;
+#else
+  cmad4_top(acc, cnt, a0, a1, a2, a3, b);
+#endif
+}
+
 // Same, when the mathematical bound guarantees no carry out of word 7.
 HB_HD void cmad4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -539,19 +563,30 @@ HB_HD void acc_zero(Acc& t) {
 }
 
 // t += a*b.  Caller keeps the true value below 2^512 (see acc_fold).
+// FRESH: count the chain carries through a fresh register (cmad4_cnt) -- for kernels that
+// unroll several macs back to back (interp_small_kernel); loops of one mac per iteration
+// are better off with the direct form.
+template <bool FRESH = false>
 HB_HD void acc_mac(Acc& t, const Fe& a, const Fe& b) {
+  auto chain = [](uint32_t* acc, uint32_t& cnt, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                  uint32_t d) {
+    if (FRESH)
+      cmad4_cnt(acc, cnt, a0, a1, a2, a3, d);
+    else
+      cmad4_top(acc, cnt, a0, a1, a2, a3, d);
+  };
 #pragma unroll
   for (int i = 0; i < 8; i += 2) {
     // even digit b_i: a_even*b_i -> E[i..i+8), a_odd*b_i -> O[i..i+8)
-    cmad4_top(t.e + i, t.ke[i / 2], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
-    cmad4_top(t.o + i, t.ko[i / 2], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+    chain(t.e + i, t.ke[i / 2], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
+    chain(t.o + i, t.ko[i / 2], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
     // odd digit b_{i+1}: a_odd*b -> E[i+2..i+10), a_even*b -> O[i..i+8)
     if (i + 2 < 8) {
-      cmad4_top(t.e + i + 2, t.ke[i / 2 + 1], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i + 1]);
+      chain(t.e + i + 2, t.ke[i / 2 + 1], a.w[1], a.w[3], a.w[5], a.w[7], b.w[i + 1]);
     } else {
       cmad4(t.e + 8, a.w[1], a.w[3], a.w[5], a.w[7], b.w[7]);  // top chain: value < 2^512
     }
-    cmad4_top(t.o + i, t.ko[i / 2], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i + 1]);
+    chain(t.o + i, t.ko[i / 2], a.w[0], a.w[2], a.w[4], a.w[6], b.w[i + 1]);
   }
 }
 

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) i
           Fe m;
 #pragma unroll
           for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
-          acc_mac(acc, lds_fe_reload(yrow + 2 * j), m);
+          acc_mac<true>(acc, lds_fe_reload(yrow + 2 * j), m);
           if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
         }
         r = acc_redc<F>(acc);

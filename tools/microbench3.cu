@@ -1,9 +1,8 @@
 // Micro-benchmark 3: what exactly limits the 64-bit integer multiply-add pipe on
 // the B200, and how fast is the FP64 pipe next to it?  (Feeds the choice of
 // multiplier for the next round: DESIGN.md section 4.)
-//   * IMAD.WIDE with the same / different / constant-bank multiplier operands
-//     (operand-reuse cache vs register-file reads), with and without the
-//     predicate carry chain, chains of 2 and 4
+//   * IMAD.WIDE without carries (register / constant-bank multiplier) and as
+//     predicate carry chains of 2 and 4
 //   * DFMA alone, and DFMA with the two 64-bit integer adds per product that a
 //     52-bit-limb FP64 multiplier needs
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench3 microbench3.cu
@@ -14,24 +13,29 @@
 
 struct Consts { uint32_t c[8]; };
 
-// mode 0: same a, same b   1: different a, same b   2: different a and b   3: different a, constant-bank b
+// Plain (carry-free) IMAD.WIDE accumulation.  One multiplier operand is the high word of a
+// NEIGHBOURING accumulator, so the products change every iteration: ptxas hoists loop-
+// invariant products out of the loop and turns the multiply-adds into IADD3s -- which is
+// what it did to the first version of this test (and to microbench.cu's k_imad_wide): the
+// "60 /clk/SM" those reported was the integer ADD rate.
+// mode 0: second operand in a register   1: second operand from the constant bank
 template <int MODE>
 __global__ void __launch_bounds__(256) k_wide(uint32_t* o, int iters, uint32_t m0, const __grid_constant__ Consts cc) {
   uint64_t acc[8];
-  uint32_t a[8], b[8];
+  uint32_t b[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    acc[c] = c + threadIdx.x;
-    a[c] = threadIdx.x * 2654435761u + 1 + (MODE >= 1 ? c * 40503u : 0);
-    b[c] = m0 + (MODE == 2 ? c * 7919u : 0);
+    acc[c] = ((uint64_t)(threadIdx.x * 2654435761u + 1 + c * 40503u) << 32) | (c + threadIdx.x);
+    b[c] = m0 + c * 7919u;
   }
   for (int t = 0; t < iters; t++) {
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-      if (MODE == 3)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a[c]), "r"(cc.c[c]));
+      const uint32_t a = (uint32_t)(acc[(c + 1) & 7] >> 32);  // changes every iteration
+      if (MODE == 1)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(cc.c[c]));
       else
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a[c]), "r"(b[c]));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b[c]));
     }
   }
   uint64_t r = 0;
@@ -183,10 +187,8 @@ int main() {
       double ops = ops_per_thread_iter * iters * (double)blocks * 256;
       printf("%-44s %9.1f Gop/s  (%6.2f /clk/SM)\n", name, ops / ms / 1e6, ops / (ms * 1e-3) / clk / sms);
     };
-    rep("IMAD.WIDE same a, same b", 8, time_ms([&] { k_wide<0><<<blocks, 256>>>(o, iters, 12345u, cc); }));
-    rep("IMAD.WIDE diff a, same b", 8, time_ms([&] { k_wide<1><<<blocks, 256>>>(o, iters, 12345u, cc); }));
-    rep("IMAD.WIDE diff a, diff b", 8, time_ms([&] { k_wide<2><<<blocks, 256>>>(o, iters, 12345u, cc); }));
-    rep("IMAD.WIDE diff a, const-bank b", 8, time_ms([&] { k_wide<3><<<blocks, 256>>>(o, iters, 12345u, cc); }));
+    rep("IMAD.WIDE + 64-bit ALU add, no carry chain (reg b)", 8, time_ms([&] { k_wide<0><<<blocks, 256>>>(o, iters, 12345u, cc); }));
+    rep("IMAD.WIDE + 64-bit ALU add, no carry chain (ur b)", 8, time_ms([&] { k_wide<1><<<blocks, 256>>>(o, iters, 12345u, cc); }));
     rep("carry chains of 4 (reg b)   [imad.wide]", 16, time_ms([&] { k_chain<4, false><<<blocks, 256>>>(o, iters, 12345u, cc); }));
     rep("carry chains of 4 (const b) [imad.wide]", 16, time_ms([&] { k_chain<4, true><<<blocks, 256>>>(o, iters, 12345u, cc); }));
     rep("carry chains of 2 (reg b)   [imad.wide]", 16, time_ms([&] { k_chain<2, false><<<blocks, 256>>>(o, iters, 12345u, cc); }));
