@@ -237,9 +237,19 @@ def run_b200(args):
         pending = [None] * len(gathered)
         slot_done = [None] * len(gathered)
         side = torch.cuda.Stream(device=dev)
+        # per-slot constants of the gather, marshalled once (the step loop is host-time critical)
+        slot_peers = [_native.Context.peer_array(list(h.buffer_ptrs)) for h in handles]
+        slot_mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles]
+        written_ev = [torch.cuda.Event() for _ in handles]
+        done_ev = [torch.cuda.Event() for _ in handles]
+    zs32 = np.ascontiguousarray(ZS, dtype=np.int32)
     stream.synchronize()
 
-    names = {}
+    names = {"encode": ctx.last_kernel()}  # the set-up loop above ended with an encode
+    c_ptr = [t.data_ptr() for t in c]
+    e_ptr = [t.data_ptr() for t in e]
+    y_ptr = [t.data_ptr() for t in y]
+    r_ptr = [t.data_ptr() for t in r]
 
     # both kernels of the step run back to back on one compute stream; for N > 1 the
     # all-gather of the decoded block runs on a side stream (see below)
@@ -256,17 +266,17 @@ def run_b200(args):
         (world == 1 and not args.serial)
     enc_stream = torch.cuda.Stream(device=dev) if overlap_encode else stream
 
+    # one context per stream (no hbg_ctx_set_stream inside the step loop: the loop is host-time
+    # critical -- a step is ~40 us of GPU work)
+    ctx_enc = _native.Context(P, device=local) if overlap_encode else ctx
+    ctx_enc.set_stream(enc_stream.cuda_stream)
+
     def step(s, evs=None):
-        ctx.set_stream(enc_stream.cuda_stream)
         if evs is not None:
             evs[0].record(enc_stream)
-        ctx.fft_batch_evaluate(omega, pt.order, c[s].data_ptr(), batch, K, N_PARTIES,
-                               e[s].data_ptr(), _native.MEM_DEVICE)
-        if "encode" not in names:
-            names["encode"] = ctx.last_kernel()
+        ctx_enc.fft_batch_evaluate(omega, pt.order, c_ptr[s], batch, K, N_PARTIES, e_ptr[s], _native.MEM_DEVICE)
         if evs is not None:
             evs[1].record(enc_stream)
-        ctx.set_stream(stream.cuda_stream)
         if evs is not None and overlap_encode:
             evs[3].record(stream)
         fused = handles and gather_mode.startswith("fused")
@@ -276,14 +286,12 @@ def run_b200(args):
             if slot_done[slot] is not None:
                 stream.wait_event(slot_done[slot])  # the previous gather into this slot is complete everywhere
         if fused:
-            use_mc = int(getattr(h, "multicast_ptr", 0) or 0) if gather_mode == "fused-multimem" else 0
-            ctx.fft_batch_interpolate_allgather(omega, pt.order, ZS, y[s].data_ptr(), batch,
-                                                list(h.buffer_ptrs), use_mc, rank)
+            use_mc = slot_mc[slot] if gather_mode == "fused-multimem" else 0
+            ctx.fft_batch_interpolate_allgather(omega, pt.order, zs32, y_ptr[s], batch,
+                                                slot_peers[slot], use_mc, rank)
         else:
-            ctx.fft_batch_interpolate(omega, pt.order, ZS, y[s].data_ptr(), batch, r[s].data_ptr(),
+            ctx.fft_batch_interpolate(omega, pt.order, zs32, y_ptr[s], batch, r_ptr[s],
                                       _native.MEM_DEVICE)
-        if "interpolate" not in names:
-            names["interpolate"] = ctx.last_kernel()
         if evs is not None:
             evs[2].record(stream)
         if handles:
@@ -291,22 +299,20 @@ def run_b200(args):
             # device-side barrier over the symmetric-memory signal pads; it runs on a side
             # stream so this rank's next encode does not wait for the slowest rank
             slot = s % len(gathered)
-            written = torch.cuda.Event()
+            written = written_ev[slot]
             written.record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(written)
-                if not fused:
-                    # copy kernel: a few CTAs push this rank's block into every rank's buffer
-                    # (multimem.st -> replicated by the NVSwitch) while `stream` moves on
-                    ctx.set_stream(side.cuda_stream)
-                    ctx.allgather_block(r[s].data_ptr(), batch * K * E, list(handles[slot].buffer_ptrs),
-                                        int(getattr(handles[slot], "multicast_ptr", 0) or 0)
-                                        if gather_mode == "multimem-copy" else 0,
-                                        rank * batch * K * E, args.gather_ctas)
-                    ctx.set_stream(stream.cuda_stream)
-                handles[slot].barrier()
-                slot_done[slot] = torch.cuda.Event()
-                slot_done[slot].record(side)
+            side.wait_event(written)
+            if not fused:
+                # copy kernel: a few CTAs push this rank's block into every rank's buffer
+                # (multimem.st -> replicated by the NVSwitch) while `stream` moves on
+                ctx.set_stream(side.cuda_stream)
+                ctx.allgather_block(r_ptr[s], batch * K * E, slot_peers[slot],
+                                    slot_mc[slot] if gather_mode == "multimem-copy" else 0,
+                                    rank * batch * K * E, args.gather_ctas)
+                ctx.set_stream(stream.cuda_stream)
+            handles[slot].barrier()  # on torch's current stream = `side` (set around the step loops)
+            slot_done[slot] = done_ev[slot]
+            slot_done[slot].record(side)
         elif world > 1:
             # the one collective of the path: reassemble the decoded blocks on every rank.
             # It runs on NCCL's stream and overlaps the next step's kernels; the buffer
@@ -326,16 +332,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
+    # torch's *current* stream only matters for the symmetric-memory barrier of the fused
+    # gather (our kernels and events name their streams explicitly): make it `side` once
+    # instead of entering a stream context on every step
+    with torch.cuda.stream(side if handles else stream):
         sampler = ClockSampler(local)
         sampler.start()
         for i in range(args.warmup):
             step(i % sets)
+            if i == 0:
+                names["interpolate"] = ctx.last_kernel()
         barrier()
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        # per-kernel events: every step when the kernels run in order on one stream; with
+        # overlapped streams only every `--event-every`-th step (they cost host time, and for
+        # N = 1 the roofline durations come from the serial pass anyway)
+        ev_every = 1 if not overlap_encode else max(1, args.event_every)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] if i % ev_every == 0 else None
+               for i in range(args.steps)]
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
-        launches0 = ctx.launch_count()
+        launches0 = ctx.launch_count() + (ctx_enc.launch_count() if ctx_enc is not ctx else 0)
         barrier()
         host_t0 = time.perf_counter()
         t_start.record(stream)
@@ -343,20 +359,23 @@ def run_b200(args):
             step((args.warmup + i) % sets, evs[i])
         stream.wait_stream(enc_stream)
         t_end.record(stream)
+        host_enqueued = time.perf_counter()
         barrier()
         host_t1 = time.perf_counter()
-        launches = ctx.launch_count() - launches0
+        launches = ctx.launch_count() + (ctx_enc.launch_count() if ctx_enc is not ctx else 0) - launches0
         serial_evs = None
         if world == 1 and overlap_encode:
             # serial pass (not part of `value`): the same steps with both kernels on one stream,
             # so each kernel's CUDA-event duration is its own
             enc_stream_saved, enc_stream = enc_stream, stream
+            ctx_enc.set_stream(stream.cuda_stream)
             serial_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)]
                           for _ in range(min(args.steps, 200))]
             for i, ev in enumerate(serial_evs):
                 step((args.warmup + i) % sets, ev)
             barrier()
             enc_stream = enc_stream_saved
+            ctx_enc.set_stream(enc_stream.cuda_stream)
         sampler.stop_flag.set()
         sampler.join()
     total_ms = t_start.elapsed_time(t_end)
@@ -364,8 +383,9 @@ def run_b200(args):
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-    enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / args.steps
-    dec_ms = sum(ev[3 if overlap_encode else 1].elapsed_time(ev[2]) for ev in evs) / args.steps
+    timed = [ev for ev in evs if ev is not None]
+    enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in timed) / len(timed)
+    dec_ms = sum(ev[3 if overlap_encode else 1].elapsed_time(ev[2]) for ev in timed) / len(timed)
     overlapped_ms = None
     if serial_evs is not None:
         overlapped_ms = {"encode": enc_ms, "interpolate": dec_ms}
@@ -505,6 +525,7 @@ def run_b200(args):
                            if world > 1 else ""),
                        "polys_per_s": value / K},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "host_enqueue_ms_per_step": (host_enqueued - host_t0) * 1e3 / args.steps,
             "clocks": sampler.result(host_t0, host_t1),
         }
         print(json.dumps(line), flush=True)
@@ -523,6 +544,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--sets", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--event-every", type=int, default=8,
+                    help="with overlapped streams: record per-kernel events on every n-th step only")
     ap.add_argument("--serial", action="store_true",
                     help="N=1: run the two kernels of a step back to back on one stream")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "copy", "nccl"],

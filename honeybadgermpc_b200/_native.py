@@ -219,13 +219,19 @@ class Context:
     def fft_batch_interpolate_allgather(self, omega, n, zs, ys, batch, peer_ptrs, multicast_ptr, rank):
         """device pointers only; peer_ptrs: one pointer per rank (ints)"""
         zs = np.ascontiguousarray(zs, dtype=np.int32)
-        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else self.peer_array(peer_ptrs)
         self._check(self.lib.hbg_fft_batch_interpolate_allgather(
             self.handle, _ptr(omega), n, _ptr(zs), len(zs), _ptr(ys), batch, arr,
             int(multicast_ptr) if multicast_ptr else None, len(peer_ptrs), rank))
 
+    @staticmethod
+    def peer_array(peer_ptrs):
+        """marshal the per-rank buffer pointers once; the result can be passed wherever
+        `peer_ptrs` is expected (hot loops call with the same buffers every step)"""
+        return (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+
     def allgather_block(self, block_ptr, nbytes, peer_ptrs, multicast_ptr, offset_bytes, max_ctas=0):
-        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else self.peer_array(peer_ptrs)
         self._check(self.lib.hbg_allgather_block(
             self.handle, int(block_ptr), nbytes, arr, int(multicast_ptr) if multicast_ptr else None,
             offset_bytes, len(peer_ptrs), max_ctas))

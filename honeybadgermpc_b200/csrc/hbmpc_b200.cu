@@ -406,7 +406,8 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
     memset(&a.gather, 0, sizeof(a.gather));
   }
   memcpy(a.m, m.data(), sizeof(a.m));
-  {  // the same matrix for the radix-2^29 arithmetic: limbs of M[i][j] * 2^261 mod p
+  const int arith_env = ctx->matvec_path == 4 ? 1 : 0;
+  if (arith_env == 1) {  // the same matrix for the radix-2^29 arithmetic: limbs of M[i][j] * 2^261 mod p
     const HostField& f = *ctx->field;
     Fe r261;
     memcpy(r261.w, ctx->fp.r261, 32);
@@ -416,7 +417,6 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
       to_limbs29(f.mul(v, r261), a.m29[e / K][e % K]);
     }
   }
-  const int arith_env = ctx->matvec_path == 4 ? 1 : 0;
   // two warps share 32 rows for K >= 4 (each thread K/2 outputs), one thread per row below
   constexpr int ROWS = 64, SPLIT = K >= 4 ? 2 : 1;
   const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;

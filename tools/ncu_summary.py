@@ -16,6 +16,9 @@ WANT = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
     "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
     "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed.sum",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
@@ -26,6 +29,8 @@ WANT = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
 ]
 
 
