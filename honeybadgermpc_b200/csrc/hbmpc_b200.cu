@@ -47,7 +47,8 @@ struct hbg_ctx {
   int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel,
                         // 4 ntt with the register-resident split kernel for n = 16
   int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel,
-                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic
+                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic, 5 ... with Karatsuba
+  int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
   std::string err;
   uint64_t launches = 0;
   const char* last_kernel = "";
@@ -405,33 +406,40 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
   } else {
     memset(&a.gather, 0, sizeof(a.gather));
   }
-  memcpy(a.m, m.data(), sizeof(a.m));
-  const int arith_env = ctx->matvec_path == 4 ? 1 : 0;
-  if (arith_env == 1) {  // the same matrix for the radix-2^29 arithmetic: limbs of M[i][j] * 2^261 mod p
-    const HostField& f = *ctx->field;
-    Fe r261;
-    memcpy(r261.w, ctx->fp.r261, 32);
-    for (int e = 0; e < K * K; e++) {
-      Fe v;
-      memcpy(v.w, &m[(size_t)e * 8], 32);
-      to_limbs29(f.mul(v, r261), a.m29[e / K][e % K]);
+  // 0: 32-bit-limb lazy accumulator, 1: radix 2^29 (path 4), 2: Karatsuba (path 5)
+  const int arith = ctx->matvec_path == 4 ? 1 : ctx->matvec_path == 5 ? 2 : ctx->interp_arith;
+  for (int e = 0; e < K * K; e++) {
+    Fe v;
+    memcpy(v.w, &m[(size_t)e * 8], 32);
+    uint32_t* dst = a.mc[e / K][e % K];
+    if (arith == 1) {  // limbs of M[i][j] * 2^261 mod p
+      Fe r261;
+      memcpy(r261.w, ctx->fp.r261, 32);
+      to_limbs29(ctx->field->mul(v, r261), dst);
+    } else if (arith == 2) {
+      KConst c;
+      kconst_from_mont(v, &c);
+      memcpy(dst, c.b, 32);
+      memcpy(dst + 8, c.sb, 16);
+      dst[12] = c.cb;
+    } else {
+      memcpy(dst, v.w, 32);
     }
   }
   // two warps share 32 rows for K >= 4 (each thread K/2 outputs), one thread per row below
   constexpr int ROWS = 64, SPLIT = K >= 4 ? 2 : 1;
   const size_t in_tile = (size_t)ROWS * K * 32, out_tile = (size_t)ROWS * ((2 * K) | 1) * 16;
   const unsigned grid = (unsigned)((batch + ROWS - 1) / ROWS);
-  if (gather) {  // fused all-gather: results go through a shared tile to every rank's buffer
-    if (arith_env == 1)
-      interp_small_kernel<F, K, ROWS, SPLIT, true, 1><<<grid, ROWS * SPLIT, in_tile + out_tile, ctx->stream>>>(a);
-    else
-      interp_small_kernel<F, K, ROWS, SPLIT, true, 0><<<grid, ROWS * SPLIT, in_tile + out_tile, ctx->stream>>>(a);
-  } else {       // local output: one 256-bit store per element straight from registers
-    if (arith_env == 1)
-      interp_small_kernel<F, K, ROWS, SPLIT, false, 1><<<grid, ROWS * SPLIT, in_tile, ctx->stream>>>(a);
-    else
-      interp_small_kernel<F, K, ROWS, SPLIT, false, 0><<<grid, ROWS * SPLIT, in_tile, ctx->stream>>>(a);
-  }
+  auto go = [&](auto arith_c) {
+    constexpr int A = decltype(arith_c)::value;
+    if (gather)  // fused all-gather: results go through a shared tile to every rank's buffer
+      interp_small_kernel<F, K, ROWS, SPLIT, true, A><<<grid, ROWS * SPLIT, in_tile + out_tile, ctx->stream>>>(a);
+    else         // local output: one 256-bit store per element straight from registers
+      interp_small_kernel<F, K, ROWS, SPLIT, false, A><<<grid, ROWS * SPLIT, in_tile, ctx->stream>>>(a);
+  };
+  if (arith == 2) go(std::integral_constant<int, 2>{});
+  else if (arith == 1) go(std::integral_constant<int, 1>{});
+  else go(std::integral_constant<int, 0>{});
   return HBG_OK;
 }
 
@@ -832,6 +840,10 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
   ctx->field = new HostField(fp);
   ctx->is_bls = true;
   for (int i = 0; i < 8; i++) ctx->is_bls = ctx->is_bls && fp.p[i] == FieldBLS::p(i);
+  if (const char* ar = getenv("HBG_INTERP_ARITH")) {  // experiments: default arithmetic of the small-k kernel
+    int v = atoi(ar);
+    if (v >= 0 && v <= 2) ctx->interp_arith = v;
+  }
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx->field;
     delete ctx;
@@ -905,7 +917,7 @@ uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches :
 const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 4) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 5) return HBG_ERR_INVALID;
   ctx->matvec_path = path;
   return HBG_OK;
 }

@@ -480,8 +480,11 @@ struct SmallInterpArgs {
   unsigned long long batch;
   unsigned long long gather_row0;  // first row of this rank inside the gathered array
   GatherDst gather;                // world == 0: plain local output
-  uint32_t m[K][K][8];             // M[i][j], Montgomery form (R = 2^256): ARITH 0
-  uint32_t m29[K][K][9];           // M[i][j] * 2^261 mod p as 9 x 29-bit limbs: ARITH 1
+  // M[i][j] in the form the arithmetic wants (13 words reserved per entry):
+  //   ARITH 0: 8 words, Montgomery form (R = 2^256)
+  //   ARITH 1: 9 limbs of 29 bits of M * 2^261 mod p
+  //   ARITH 2: KConst (rowmath.cuh): the 8 Montgomery words, (B0 + B1) mod 2^128 and its carry
+  uint32_t mc[K][K][13];
 };
 
 // ROWS rows per CTA, SPLIT warps share a row (warp w handles the outputs
@@ -492,11 +495,15 @@ struct SmallInterpArgs {
 // store (a whole 32-byte sector).  GATHER = true (fused all-gather): results are
 // parked in a shared tile and streamed to every rank with consecutive 16-byte
 // multimem / peer stores, which keeps the NVLink packets large.
-// ARITH = 1 (default): carry-free radix-2^29 accumulation (rowmath.cuh: mac29 / redc29),
-// plain IMAD.WIDE at twice the issue rate of the carry-chained form.  ARITH = 0: the
-// 32-bit-limb lazy accumulator of fp256.cuh (Acc), kept as a bit-identical second path.
+// ARITH = 0: the 32-bit-limb lazy accumulator of fp256.cuh (Acc): 64 IMAD.WIDE per term.
+// ARITH = 1: carry-free radix-2^29 accumulation (rowmath.cuh: mac29 / redc29): 81 plain
+//            IMAD.WIDE per term, far fewer ALU instructions; same speed as 0 on the B200
+//            (IMAD.WIDE costs 4 pipe cycles with or without a carry chain).
+// ARITH = 2: Karatsuba (rowmath.cuh: kara_mac / kara_finish): 48 IMAD.WIDE per term, three
+//            accumulators (~60 registers) combined once per output.
+// All three are bit-identical (tests/test_gpu_ntl.py runs them against the oracle).
 template <class F, int K, int ROWS, int SPLIT, bool GATHER, int ARITH>
-__global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
+__global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? (ARITH == 2 ? 5 : 7) : 1)) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
   constexpr int THREADS = ROWS * SPLIT;
   extern __shared__ uint4 smem[];
   __shared__ alignas(8) uint64_t bar;
@@ -525,7 +532,23 @@ __global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) i
     const int i = i0 + part;
     if (i < K) {
       Fe r;
-      if (ARITH == 1) {
+      if (ARITH == 2) {
+        KAcc kl, kh, km;
+        kacc_zero(kl);
+        kacc_zero(kh);
+        kacc_zero(km);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          KConst c;
+#pragma unroll
+          for (int q = 0; q < 8; q++) c.b[q] = a.mc[i][j][q];
+#pragma unroll
+          for (int q = 0; q < 4; q++) c.sb[q] = a.mc[i][j][8 + q];
+          c.cb = a.mc[i][j][12];
+          kara_mac(kl, kh, km, lds_fe_reload(yrow + 2 * j), c);
+        }
+        r = kara_finish<F>(kl, kh, km);
+      } else if (ARITH == 1) {
         uint64_t col[17];
 #pragma unroll
         for (int c = 0; c < 17; c++) col[c] = 0;
@@ -534,7 +557,7 @@ __global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) i
           uint32_t y[9], m[9];
           to_limbs29(lds_fe_reload(yrow + 2 * j), y);
 #pragma unroll
-          for (int q = 0; q < 9; q++) m[q] = a.m29[i][j][q];
+          for (int q = 0; q < 9; q++) m[q] = a.mc[i][j][q];
           mac29(col, y, m);
         }
         if (K > 6) norm29(col);  // 7 or 8 terms: make room for the reduction products
@@ -546,7 +569,7 @@ __global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) i
         for (int j = 0; j < K; j++) {
           Fe m;
 #pragma unroll
-          for (int q = 0; q < 8; q++) m.w[q] = a.m[i][j][q];
+          for (int q = 0; q < 8; q++) m.w[q] = a.mc[i][j][q];
           acc_mac<true>(acc, lds_fe_reload(yrow + 2 * j), m);
           if ((j + 1) % F::kFold == 0 || j == K - 1) acc_fold<F>(acc);
         }
