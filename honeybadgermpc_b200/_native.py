@@ -193,7 +193,7 @@ class Context:
 
     def set_matvec_path(self, path):
         self._check(self.lib.hbg_ctx_set_matvec_path(
-            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3, "small-r29": 4, "small-kara": 5}[path]))
+            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3, "small-r29": 4}[path]))
 
     # -- batch operations (limb arrays or device pointers) ------------------
     def vandermonde_batch_evaluate(self, xs, polys, batch, d, out, mem=MEM_HOST):

@@ -47,7 +47,7 @@ struct hbg_ctx {
   int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel,
                         // 4 ntt with the register-resident split kernel for n = 16
   int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel,
-                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic, 5 ... with Karatsuba
+                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic
   int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
   std::string err;
   uint64_t launches = 0;
@@ -406,8 +406,8 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
   } else {
     memset(&a.gather, 0, sizeof(a.gather));
   }
-  // 0: 32-bit-limb lazy accumulator, 1: radix 2^29 (path 4), 2: Karatsuba (path 5)
-  const int arith = ctx->matvec_path == 4 ? 1 : ctx->matvec_path == 5 ? 2 : ctx->interp_arith;
+  // 0: 32-bit-limb lazy accumulator, 1: radix 2^29 (path 4)
+  const int arith = ctx->matvec_path == 4 ? 1 : ctx->interp_arith;
   for (int e = 0; e < K * K; e++) {
     Fe v;
     memcpy(v.w, &m[(size_t)e * 8], 32);
@@ -416,12 +416,6 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
       Fe r261;
       memcpy(r261.w, ctx->fp.r261, 32);
       to_limbs29(ctx->field->mul(v, r261), dst);
-    } else if (arith == 2) {
-      KConst c;
-      kconst_from_mont(v, &c);
-      memcpy(dst, c.b, 32);
-      memcpy(dst + 8, c.sb, 16);
-      dst[12] = c.cb;
     } else {
       memcpy(dst, v.w, 32);
     }
@@ -437,8 +431,7 @@ int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const vo
     else         // local output: one 256-bit store per element straight from registers
       interp_small_kernel<F, K, ROWS, SPLIT, false, A><<<grid, ROWS * SPLIT, in_tile, ctx->stream>>>(a);
   };
-  if (arith == 2) go(std::integral_constant<int, 2>{});
-  else if (arith == 1) go(std::integral_constant<int, 1>{});
+  if (arith == 1) go(std::integral_constant<int, 1>{});
   else go(std::integral_constant<int, 0>{});
   return HBG_OK;
 }
@@ -842,7 +835,7 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
   for (int i = 0; i < 8; i++) ctx->is_bls = ctx->is_bls && fp.p[i] == FieldBLS::p(i);
   if (const char* ar = getenv("HBG_INTERP_ARITH")) {  // experiments: default arithmetic of the small-k kernel
     int v = atoi(ar);
-    if (v >= 0 && v <= 2) ctx->interp_arith = v;
+    if (v >= 0 && v <= 1) ctx->interp_arith = v;
   }
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx->field;
@@ -917,7 +910,7 @@ uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches :
 const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 5) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 4) return HBG_ERR_INVALID;
   ctx->matvec_path = path;
   return HBG_OK;
 }

@@ -232,18 +232,4 @@ inline bool vandermonde_inverse(const HostField& f, const std::vector<Fe>& xs,
   return true;
 }
 
-// Prepared constant of the Karatsuba dot product (rowmath.cuh: KConst) from a
-// Montgomery-form matrix entry.  Declared here (host only) to keep rowmath.cuh free of it.
-template <class KC>
-inline void kconst_from_mont(const Fe& m, KC* out) {
-  uint64_t c = 0;
-  for (int i = 0; i < 8; i++) out->b[i] = m.w[i];
-  for (int i = 0; i < 4; i++) {
-    c += (uint64_t)m.w[i] + m.w[4 + i];
-    out->sb[i] = (uint32_t)c;
-    c >>= 32;
-  }
-  out->cb = (uint32_t)c;
-}
-
 }  // namespace hb

@@ -177,25 +177,4 @@ int hbt_dot29(const uint64_t* p, int n, const uint64_t* a, const uint64_t* b, in
   return 0;
 }
 
-// out = sum_j a[j]*b[j] mod p (n <= 8) through the Karatsuba lazy accumulator
-// (kara_mac / kara_finish): a standard form, b converted to Montgomery form and prepared here.
-int hbt_dot_kara(const uint64_t* p, int n, const uint64_t* a, const uint64_t* b, uint64_t* out) {
-  FieldParams fp;
-  if (!field_params_init(p, &fp)) return 1;
-  if (n > 8) return 3;
-  HostField f(fp);
-  HostField::Scope s(&fp);
-  KAcc l, h, m;
-  kacc_zero(l);
-  kacc_zero(h);
-  kacc_zero(m);
-  for (int j = 0; j < n; j++) {
-    KConst c;
-    kconst_from_mont(f.to_mont(fe_from_u64(b + 4 * j)), &c);
-    kara_mac(l, h, m, fe_from_u64(a + 4 * j), c);
-  }
-  fe_to_u64(kara_finish<FieldHost>(l, h, m), out);
-  return 0;
-}
-
 }  // extern "C"

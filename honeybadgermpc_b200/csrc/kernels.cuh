@@ -480,11 +480,10 @@ struct SmallInterpArgs {
   unsigned long long batch;
   unsigned long long gather_row0;  // first row of this rank inside the gathered array
   GatherDst gather;                // world == 0: plain local output
-  // M[i][j] in the form the arithmetic wants (13 words reserved per entry):
+  // M[i][j] in the form the arithmetic wants (9 words reserved per entry):
   //   ARITH 0: 8 words, Montgomery form (R = 2^256)
   //   ARITH 1: 9 limbs of 29 bits of M * 2^261 mod p
-  //   ARITH 2: KConst (rowmath.cuh): the 8 Montgomery words, (B0 + B1) mod 2^128 and its carry
-  uint32_t mc[K][K][13];
+  uint32_t mc[K][K][9];
 };
 
 // ROWS rows per CTA, SPLIT warps share a row (warp w handles the outputs
@@ -499,11 +498,12 @@ struct SmallInterpArgs {
 // ARITH = 1: carry-free radix-2^29 accumulation (rowmath.cuh: mac29 / redc29): 81 plain
 //            IMAD.WIDE per term, far fewer ALU instructions; same speed as 0 on the B200
 //            (IMAD.WIDE costs 4 pipe cycles with or without a carry chain).
-// ARITH = 2: Karatsuba (rowmath.cuh: kara_mac / kara_finish): 48 IMAD.WIDE per term, three
-//            accumulators (~60 registers) combined once per output.
-// All three are bit-identical (tests/test_gpu_ntl.py runs them against the oracle).
+// Both are bit-identical (tests/test_gpu_ntl.py runs them against the oracle).  A third,
+// Karatsuba (48 IMAD.WIDE per term, three accumulators combined once per output), was
+// bit-exact too but needed 96 registers and 1 992 instructions per output: 46 us against
+// 36 us at 65 536 rows; it is not kept.
 template <class F, int K, int ROWS, int SPLIT, bool GATHER, int ARITH>
-__global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? (ARITH == 2 ? 5 : 7) : 1)) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
+__global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? 7 : 1)) interp_small_kernel(const __grid_constant__ SmallInterpArgs<K> a) {
   constexpr int THREADS = ROWS * SPLIT;
   extern __shared__ uint4 smem[];
   __shared__ alignas(8) uint64_t bar;
@@ -532,23 +532,7 @@ __global__ void __launch_bounds__(ROWS * SPLIT, (ROWS * SPLIT == 128 ? (ARITH ==
     const int i = i0 + part;
     if (i < K) {
       Fe r;
-      if (ARITH == 2) {
-        KAcc kl, kh, km;
-        kacc_zero(kl);
-        kacc_zero(kh);
-        kacc_zero(km);
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-          KConst c;
-#pragma unroll
-          for (int q = 0; q < 8; q++) c.b[q] = a.mc[i][j][q];
-#pragma unroll
-          for (int q = 0; q < 4; q++) c.sb[q] = a.mc[i][j][8 + q];
-          c.cb = a.mc[i][j][12];
-          kara_mac(kl, kh, km, lds_fe_reload(yrow + 2 * j), c);
-        }
-        r = kara_finish<F>(kl, kh, km);
-      } else if (ARITH == 1) {
+      if (ARITH == 1) {
         uint64_t col[17];
 #pragma unroll
         for (int c = 0; c < 17; c++) col[c] = 0;

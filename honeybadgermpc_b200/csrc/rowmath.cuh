@@ -212,185 +212,4 @@ HB_HD Fe redc29(uint64_t* col) {
   return r;
 }
 
-// ---------------------------------------------------------------------------
-// Karatsuba lazy dot products (k <= 8 terms).
-//
-// a = A0 + A1 W, b = B0 + B1 W (W = 2^128):
-//   a b = L + (M - L - H) W + H W^2,  L = A0 B0, H = A1 B1, M = (A0 + A1)(B0 + B1)
-// Three 4x4-limb products (48 IMAD.WIDE) instead of one 8x8 (64).  The sums over the
-// terms of a dot product are accumulated separately (KAcc x 3) and combined ONCE per
-// output, so the extra additions of Karatsuba are paid per output, not per term.
-// The 129th bits: A0 + A1 = sa + ca W, B0 + B1 = sb + cb W (sb, cb precomputed with the
-// constant), M = sa sb + (ca sb + cb sa) W + ca cb W^2 -- the last two are plain additions
-// into M's words 4.. / 8.
-//
-// KAcc: value = sum e[w] 2^(32 w) + sum o[w] 2^(32 (w+1)) + deferred chain carries
-// k4, k6, k8 (words 4, 6, 8) and q4, q6 (words 5, 7).  Products x_i y_d sit on E when
-// i + d is even, on O when odd, two per chain (cmad2_cnt).
-// ---------------------------------------------------------------------------
-struct KAcc {
-  uint32_t e[8];
-  uint32_t o[6];
-  uint32_t k4, k6, k8, q4, q6;
-};
-
-struct KConst {      // one matrix entry, Montgomery form (R = 2^256), prepared on the host
-  uint32_t b[8];     // B0 = b[0..4), B1 = b[4..8)
-  uint32_t sb[4];    // (B0 + B1) mod 2^128
-  uint32_t cb;       // carry of B0 + B1
-};
-
-HB_HD void kacc_zero(KAcc& q) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) q.e[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 6; i++) q.o[i] = 0;
-  q.k4 = q.k6 = q.k8 = q.q4 = q.q6 = 0;
-}
-
-// acc[0..4) += a_lo * b + ((a_hi * b) << 64); the carry out of word 3 is added to cnt
-// (through a fresh register: see cmad4_cnt)
-HB_HD void cmad2_cnt(uint32_t* acc, uint32_t& cnt, uint32_t a_lo, uint32_t a_hi, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-  uint32_t cy;
-  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
-      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
-      "addc.u32 %4, 0, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(cy)
-      : "r"(a_lo), "r"(a_hi), "r"(b));
-  cnt += cy;
-#else
-  const uint64_t p0 = (uint64_t)a_lo * b, p1 = (uint64_t)a_hi * b;
-  uint64_t t = (uint64_t)acc[0] + (uint32_t)p0;
-  acc[0] = (uint32_t)t;
-  t = (uint64_t)acc[1] + (uint32_t)(p0 >> 32) + (t >> 32);
-  acc[1] = (uint32_t)t;
-  t = (uint64_t)acc[2] + (uint32_t)p1 + (t >> 32);
-  acc[2] = (uint32_t)t;
-  t = (uint64_t)acc[3] + (uint32_t)(p1 >> 32) + (t >> 32);
-  acc[3] = (uint32_t)t;
-  cnt += (uint32_t)(t >> 32);
-#endif
-}
-
-// q += x * y, x and y four 32-bit limbs each
-HB_HD void kacc_mac(KAcc& q, const uint32_t* x, const uint32_t* y) {
-  cmad2_cnt(q.e + 0, q.k4, x[0], x[2], y[0]);  // positions 0, 2
-  cmad2_cnt(q.o + 0, q.q4, x[1], x[3], y[0]);  // positions 1, 3
-  cmad2_cnt(q.e + 2, q.k6, x[1], x[3], y[1]);  // positions 2, 4
-  cmad2_cnt(q.o + 0, q.q4, x[0], x[2], y[1]);  // positions 1, 3
-  cmad2_cnt(q.e + 2, q.k6, x[0], x[2], y[2]);  // positions 2, 4
-  cmad2_cnt(q.o + 2, q.q6, x[1], x[3], y[2]);  // positions 3, 5
-  cmad2_cnt(q.e + 4, q.k8, x[1], x[3], y[3]);  // positions 4, 6
-  cmad2_cnt(q.o + 2, q.q6, x[0], x[2], y[3]);  // positions 3, 5
-}
-
-// r[0..n) = x + y + cin, returns carry (n-word add, plain C: ptxas turns it into IADD3.X chains)
-template <int N>
-HB_HD uint32_t addn(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin = 0) {
-  uint64_t c = cin;
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    c += (uint64_t)x[i] + y[i];
-    r[i] = (uint32_t)c;
-    c >>= 32;
-  }
-  return (uint32_t)c;
-}
-
-template <int N>
-HB_HD uint32_t subn(uint32_t* r, const uint32_t* x, const uint32_t* y) {  // returns borrow
-  uint32_t bw = 0;
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    const uint64_t d = (uint64_t)x[i] - y[i] - bw;
-    r[i] = (uint32_t)d;
-    bw = (uint32_t)(d >> 32) & 1u;
-  }
-  return bw;
-}
-
-// the accumulated value as 9 words (callers keep it below 2^288)
-HB_HD void kacc_value(const KAcc& q, uint32_t* v) {
-  uint32_t x[9], y[9];
-#pragma unroll
-  for (int i = 0; i < 8; i++) x[i] = q.e[i];
-  x[8] = q.k8;
-  y[0] = 0;
-#pragma unroll
-  for (int i = 0; i < 6; i++) y[i + 1] = q.o[i];
-  y[7] = q.q6;
-  y[8] = 0;
-  addn<9>(v, x, y);
-  // remaining deferred carries: k4 (word 4), q4 (word 5), k6 (word 6)
-  uint32_t z[9];
-#pragma unroll
-  for (int i = 0; i < 9; i++) z[i] = 0;
-  z[4] = q.k4;
-  z[5] = q.q4;
-  z[6] = q.k6;
-  addn<9>(v, v, z);
-}
-
-// One term of a Karatsuba dot product: a is data (standard form, canonical), c the
-// prepared constant.  l, h, m accumulate L, H and M (see above).
-HB_HD void kara_mac(KAcc& l, KAcc& h, KAcc& m, const Fe& a, const KConst& c) {
-  kacc_mac(l, a.w, c.b);
-  kacc_mac(h, a.w + 4, c.b + 4);
-  uint32_t sa[4];
-  const uint32_t ca = addn<4>(sa, a.w, a.w + 4);
-  kacc_mac(m, sa, c.sb);
-  // (ca * sb + cb * sa) W + ca cb W^2, added into m's E words 4..7 and the word-8 counter
-  uint32_t t[4];
-  const uint32_t ma = 0u - ca, mb = 0u - c.cb;
-#pragma unroll
-  for (int i = 0; i < 4; i++) t[i] = c.sb[i] & ma;
-  m.k8 += addn<4>(m.e + 4, m.e + 4, t);
-#pragma unroll
-  for (int i = 0; i < 4; i++) t[i] = sa[i] & mb;
-  m.k8 += addn<4>(m.e + 4, m.e + 4, t);
-  m.k8 += ca & c.cb;
-}
-
-// Combine the three sums of a dot product of at most 8 terms (canonical data, constants
-// < p) into sum a_j b_j / R mod p, canonical:  T = L + (M - L - H) W + H W^2 < 8 p^2, its
-// high half (9 words) is brought below p by conditional subtractions of 2p and p, then
-// the usual Montgomery reduction of the lazy accumulator (acc_redc).
-template <class F>
-HB_HD Fe kara_finish(const KAcc& l, const KAcc& h, const KAcc& m) {
-  uint32_t lv[9], hv[9], mid[9];
-  kacc_value(l, lv);
-  kacc_value(h, hv);
-  kacc_value(m, mid);
-  subn<9>(mid, mid, lv);
-  subn<9>(mid, mid, hv);  // = sum (A0 B1 + A1 B0) >= 0
-  // T (17 words) = lv + (mid << 128) + (hv << 256)
-  uint32_t t[17], u[17];
-#pragma unroll
-  for (int i = 0; i < 17; i++) {
-    t[i] = i < 9 ? lv[i] : 0u;
-    u[i] = (i >= 4 && i < 13) ? mid[i - 4] : 0u;
-  }
-  addn<17>(t, t, u);
-#pragma unroll
-  for (int i = 0; i < 17; i++) u[i] = (i >= 8) ? hv[i - 8] : 0u;
-  addn<17>(t, t, u);
-  // high half t[8..17) < 4p: subtract 2p, then p, where possible
-  uint32_t p9[9], p2[9], d[9];
-  load_p<F>(p9);
-  p9[8] = 0;
-  addn<9>(p2, p9, p9);
-  uint32_t bw = subn<9>(d, t + 8, p2);
-#pragma unroll
-  for (int i = 0; i < 9; i++) t[8 + i] = bw ? t[8 + i] : d[i];
-  bw = subn<9>(d, t + 8, p9);
-#pragma unroll
-  for (int i = 0; i < 9; i++) t[8 + i] = bw ? t[8 + i] : d[i];
-  Fe lo = mont_redc_lo<F>(t);
-  Fe hi;
-#pragma unroll
-  for (int i = 0; i < 8; i++) hi.w[i] = t[8 + i];
-  return fe_add<F>(lo, hi);
-}
-
 }  // namespace hb

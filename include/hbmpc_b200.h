@@ -91,8 +91,7 @@ int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path);
  * global memory, 2 = matrix and TMA-staged input tile in shared memory,
  * 3 = k <= 8 interpolation with the matrix in the constant bank, one row per
  * thread (falls back to 0 where it does not apply), 4 = the same kernel with the
- * carry-free radix-2^29 accumulator instead of the 32-bit-limb carry chains,
- * 5 = the same kernel with the Karatsuba accumulator (48 limb products per term). */
+ * carry-free radix-2^29 accumulator instead of the 32-bit-limb carry chains. */
 int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path);
 
 /* vandermonde_batch_evaluate(x, polynomials, modulus), pyx:199-244 +

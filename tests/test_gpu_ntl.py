@@ -90,7 +90,7 @@ def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
     polys = [[rng.randrange(p) for _ in range(rng.randint(1, d))] for _ in range(batch)]
     polys[0] = polys[0] + [p - 1] * (d - len(polys[0]))
     want = orc.vandermonde_batch_evaluate(xs, polys, p)
-    for path in ("auto", "global", "smem", "small", "small-r29", "small-kara"):
+    for path in ("auto", "global", "smem", "small", "small-r29"):
         ntl._ctx(p).set_matvec_path(path)
         assert ntl.vandermonde_batch_evaluate(xs, polys, p) == want, path
     if p > n:
@@ -98,7 +98,7 @@ def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
         xk = rng.sample(xs, k)
         ys = [[rng.randrange(p) for _ in range(k)] for _ in range(batch)]
         want = orc.vandermonde_batch_interpolate(xk, ys, p)
-        for path in ("auto", "global", "smem", "small", "small-r29", "small-kara"):
+        for path in ("auto", "global", "smem", "small", "small-r29"):
             ntl._ctx(p).set_matvec_path(path)
             assert ntl.vandermonde_batch_interpolate(xk, ys, p) == want, path
     ntl._ctx(p).set_matvec_path("auto")
@@ -238,7 +238,7 @@ def test_config5_shard_round_trip(ntl):
     enc = ntl.fft_batch_evaluate_limbs(c, omega, P, pt.order, n)
     zs = sorted(random.Random(5).sample(range(n), k))
     ys = np.ascontiguousarray(enc[:, zs, :])
-    for path in ("auto", "global", "smem", "small-r29", "small-kara"):
+    for path in ("auto", "global", "smem", "small-r29"):
         ntl._ctx(P).set_matvec_path(path)
         assert np.array_equal(ntl.fft_batch_interpolate_limbs(zs, ys, omega, P, pt.order), c), path
     ntl._ctx(P).set_matvec_path("auto")

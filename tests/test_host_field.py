@@ -154,27 +154,6 @@ def test_lazy_dot_radix29(lib, p):
                     assert val(out) == want, (n, mode, lowones, prenorm)
 
 
-@pytest.mark.parametrize("p", [P, 13, 53, 2 ** 61 - 1, 2 ** 127 - 1, 2 ** 255 - 19, 2 ** 254 + 2 ** 128 + 45])
-def test_lazy_dot_karatsuba(lib, p):
-    # kara_mac / kara_finish (the Karatsuba row math of interp_small_kernel)
-    rng = random.Random(48)
-    out = np.zeros(4, np.uint64)
-    special = [0, 1, p - 1, 2 ** 128 - 1, 2 ** 128, (2 ** 128 - 1) * (2 ** 128 + 1) % p, 2 ** 255 % p, (p - 1) // 2]
-    for n in range(0, 9):
-        for mode in ("rand", "max", "mixed", "mixed2"):
-            if mode == "rand":
-                a = [rng.randrange(p) for _ in range(n)]
-                b = [rng.randrange(p) for _ in range(n)]
-            elif mode == "max":
-                a, b = [p - 1] * n, [p - 1] * n
-            else:
-                a = [rng.choice(special) % p for _ in range(n)]
-                b = [rng.choice(special) % p if mode == "mixed" else rng.randrange(p) for _ in range(n)]
-            want = sum(x * y for x, y in zip(a, b)) % p
-            assert lib.hbt_dot_kara(ptr(limbs(p)), n, ptr(many(a)), ptr(many(b)), ptr(out)) == 0
-            assert val(out) == want, (n, mode)
-
-
 def test_bad_modulus(lib):
     out = np.zeros(4, np.uint64)
     assert lib.hbt_mulmod(ptr(limbs(16)), ptr(limbs(1)), ptr(limbs(1)), ptr(out)) == 1
