@@ -251,19 +251,19 @@ def run_b200(args):
     y_ptr = [t.data_ptr() for t in y]
     r_ptr = [t.data_ptr() for t in r]
 
-    # both kernels of the step run back to back on one compute stream; for N > 1 the
-    # all-gather of the decoded block runs on a side stream (see below)
-    # With <= 4 ranks the fused kernel leaves SM time free while it waits on NVLink, so the
-    # (independent) encode of the step overlaps it on a second stream; at 8 ranks the kernel
-    # is NVLink-ingress bound for its whole duration and co-scheduling only slows both
-    # (measured: 2.18e10 shares/s back to back vs 1.91e10 overlapped), so they run in order.
+    # For N > 1 the all-gather of the decoded block is fused into the interpolation kernel (or runs
+    # on a side stream, see below) and the independent encode of the step runs on a second stream:
+    # the fused kernel leaves SM time free while it waits on NVLink.  Measured at 8 ranks with the
+    # current kernels: 2.19e10 shares/s with the encode overlapped, 2.02e10 in order (with the
+    # first kernels of this round it was the other way round: 1.91e10 against 2.18e10).
     # N = 1: the encode and the interpolation of a step are independent launches, so they go
     # to two streams: each kernel fills the GPU in a single wave (1024 CTAs for 1036 slots)
     # and spends ~8 us of its ~30 us ramping up and draining; on two streams the next
     # kernel's CTAs take over SM by SM as the previous kernel's CTAs retire.  The per-kernel
     # durations of the roofline come from a second, serial pass over the same steps.
-    overlap_encode = (world > 1 and world <= 4 and gather_mode.startswith("fused")) or \
-        (world == 1 and not args.serial)
+    overlap_encode = (world > 1 and gather_mode.startswith("fused")) or (world == 1 and not args.serial)
+    if args.overlap_encode != "auto":
+        overlap_encode = args.overlap_encode == "on"
     enc_stream = torch.cuda.Stream(device=dev) if overlap_encode else stream
 
     # one context per stream (no hbg_ctx_set_stream inside the step loop: the loop is host-time
@@ -544,6 +544,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--sets", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--overlap-encode", default="auto", choices=["auto", "on", "off"],
+                    help="run the encode of a step on its own stream (auto: N = 1, and N > 1 with the fused gather)")
     ap.add_argument("--event-every", type=int, default=8,
                     help="with overlapped streams: record per-kernel events on every n-th step only")
     ap.add_argument("--serial", action="store_true",
