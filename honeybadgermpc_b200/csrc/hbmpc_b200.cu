@@ -397,6 +397,7 @@ template <class F, int K>
 int launch_interp_small_t(hbg_ctx* ctx, const std::vector<uint32_t>& m, const void* d_in, void* d_out,
                           size_t batch, const GatherDst* gather, size_t gather_row0) {
   SmallInterpArgs<K> a;
+  memset(&a, 0, sizeof(a));
   a.in = (const uint4*)d_in;
   a.out = (uint4*)d_out;
   a.batch = batch;
