@@ -457,7 +457,7 @@ def run_b200(args):
 
     # ---- end to end: the C-ABI call a reference-side binding makes, HOST buffers
     # (pinned), H2D + kernel + D2H inside the timed region
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 60))
     hc = torch.from_numpy(synth(batch, K, 0xE2E + rank).view(np.int64)).pin_memory()
     he = torch.empty((batch, N_PARTIES, 4), dtype=torch.int64).pin_memory()
     hy = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
@@ -479,11 +479,14 @@ def run_b200(args):
         ctx.synchronize()
     barrier()
     t0 = time.perf_counter()
+    marks = [t0]
     for _ in range(e2e_steps):
         e2e_step()
         ctx.synchronize()
+        marks.append(time.perf_counter())
     torch.cuda.synchronize()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    per_step = sorted(b - a for a, b in zip(marks, marks[1:]))
     ctx.set_host_async(False)
     assert torch.equal(hr, hc), "end-to-end round trip mismatch"
     if world > 1:
@@ -494,6 +497,8 @@ def run_b200(args):
            "h2d_bytes_per_step": 2 * batch * K * E,
            "d2h_bytes_per_step": batch * (N_PARTIES + K) * E,
            "ms_per_step": e2e_dt * 1e3,
+           "ms_per_step_min_median_max": [per_step[0] * 1e3, per_step[len(per_step) // 2] * 1e3,
+                                          per_step[-1] * 1e3],
            "boundary": "hbg_fft_batch_evaluate + hbg_fft_batch_interpolate, HBG_MEM_HOST, pinned buffers, "
                        "host_async on, hbg_ctx_synchronize at the end of every step"}
 

@@ -1,0 +1,52 @@
+"""The driver-facing contract of bench.py that can be checked without a GPU: the
+reference arm prints ONE JSON line with the agreed keys (it times the CPU
+restatement of the reference's NTL path), non-zero ranks of a multi-rank
+reference run stay silent, and the B200 arm refuses to run without a device."""
+
+import json
+import os
+import subprocess
+import sys
+
+import torch
+from conftest import ROOT
+
+BENCH = os.path.join(ROOT, "bench.py")
+
+
+def run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, BENCH] + args, capture_output=True, text=True, cwd=ROOT,
+                          env=e, timeout=600)
+
+
+def test_reference_arm_line():
+    res = run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"])
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["metric"] == "GF(p) share reconstructions/sec at n=16,t=5" and d["unit"] == "shares/s"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] >= 1 and d["n_gpus"] == 1
+    assert d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_are_silent():
+    res = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+              env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_b200_arm_needs_a_device():
+    if torch.cuda.is_available():
+        return
+    res = run(["--steps", "1", "--warmup", "1", "--no-cpu"])
+    assert res.returncode != 0
+    assert "no CPU fallback" in res.stderr
