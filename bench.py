@@ -437,9 +437,10 @@ def run_b200(args):
         pass
     # the binding resource is the 64-bit integer multiply-add pipe: algorithmic
     # IMAD.WIDE per polynomial against the measured pipe rate
-    # (tools/microbench.cu on this pool: 7.4e12 IMAD.WIDE/s at 1965 MHz)
+    # (tools/microbench3.cu on this pool: carry chains of IMAD.WIDE at 31 per clock per SM =
+    # 9.0e12 /s at 1965 MHz; one warp-wide IMAD.WIDE holds the fmaheavy pipe for 4 cycles)
     imad = {"encode": 15 * 103, "interpolate": K * K * 64 + K * 48}
-    imad_peak = 7.4e12
+    imad_peak = 9.0e12
     imad_rate = imad[dom] * batch / (dom_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel": f"{dom}: {names[dom]}",
