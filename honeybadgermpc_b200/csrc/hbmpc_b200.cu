@@ -45,7 +45,8 @@ struct hbg_ctx {
   HostField* field = nullptr;
   bool is_bls = false;
   int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel,
-                        // 4 ntt with the register-resident split kernel for n = 16
+                        // 4 ntt with the register-resident split kernel for n = 16,
+                        // 5 ntt, n = 16 with the balanced (hand-over) form of the 4-point-group kernel
   int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel,
                         // 4 small-k kernel with the carry-free radix-2^29 arithmetic
   int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
@@ -364,11 +365,12 @@ int launch_ntt16_t(hbg_ctx* ctx, const Ntt16Args& a) {
   return HBG_OK;
 }
 
-// d <= 8: two 4-point groups per thread, results stored from registers (no output tile)
-template <class F, int D>
+// d <= 8: two 4-point groups per thread, results stored from registers (no output tile).
+// BAL: the even thread hands the odd thread two of its inputs (rowmath.cuh: ntt16_offload);
+// measured not to be a gain, so only `hbg_ctx_set_fft_path(ctx, 5)` selects it.
+template <class F, int D, bool BAL>
 int launch_ntt16_g4_t(hbg_ctx* ctx, const Ntt16Args& a) {
   constexpr int POLYS = 64;  // per CTA of 128 threads
-  constexpr bool BAL = false;  // even->odd hand-over (rowmath.cuh: ntt16_offload): measured, not a gain
   // input tile (+ hand-over slots, 4 elements per polynomial, when balancing)
   ntt16_g4_kernel<F, D, POLYS, BAL><<<(unsigned)((a.batch + POLYS - 1) / POLYS), 2 * POLYS,
                                       (size_t)POLYS * a.d * 32 + (BAL ? (size_t)POLYS * 4 * 32 : 0),
@@ -376,13 +378,18 @@ int launch_ntt16_g4_t(hbg_ctx* ctx, const Ntt16Args& a) {
   return HBG_OK;
 }
 
+template <class F, bool BAL>
+int launch_ntt16_g4_d(hbg_ctx* ctx, const Ntt16Args& a) {
+  if (a.d <= 4) return launch_ntt16_g4_t<F, 4, BAL>(ctx, a);
+  if (a.d <= 6) return launch_ntt16_g4_t<F, 6, BAL>(ctx, a);
+  return launch_ntt16_g4_t<F, 8, BAL>(ctx, a);
+}
+
 template <class F>
 int launch_ntt16_f(hbg_ctx* ctx, const Ntt16Args& a) {
   if (a.d <= 8 && a.stride == a.d && ctx->fft_path != 4) {
     ctx->last_kernel = "ntt16_g4_kernel";
-    if (a.d <= 4) return launch_ntt16_g4_t<F, 4>(ctx, a);
-    if (a.d <= 6) return launch_ntt16_g4_t<F, 6>(ctx, a);
-    return launch_ntt16_g4_t<F, 8>(ctx, a);
+    return ctx->fft_path == 5 ? launch_ntt16_g4_d<F, true>(ctx, a) : launch_ntt16_g4_d<F, false>(ctx, a);
   }
   ctx->last_kernel = "ntt16_split_kernel";
   if (a.d <= 4) return launch_ntt16_t<F, 4>(ctx, a);
@@ -917,7 +924,7 @@ int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
 }
 
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 4) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 5) return HBG_ERR_INVALID;
   ctx->fft_path = path;
   return HBG_OK;
 }

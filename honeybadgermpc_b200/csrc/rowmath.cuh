@@ -12,17 +12,11 @@
 
 namespace hb {
 
-// Lazy add / sub: inputs < p, result in [0, 2p), which fits 256 bits because
+// Lazy subtraction: inputs < p, result a + (p - b) in [0, 2p), which fits 256 bits because
 // p < 2^255 (hbg_ctx_create enforces it).  Only ever used as the DIGIT operand
 // (second argument) of mont_mul: with the multiplicand a < p every CIOS row keeps
 // t < a + p < 2p whatever the digits are, and the output is canonical again.
 // (The multiplicand side must stay below 2^256 - p.)
-HB_HD Fe fe_add_lazy(const Fe& a, const Fe& b) {
-  Fe r;
-  add8(r.w, a.w, b.w);
-  return r;
-}
-
 template <class F>
 HB_HD Fe fe_sub_lazy(const Fe& a, const Fe& b) {
   uint32_t p[8], t[8];

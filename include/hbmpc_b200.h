@@ -84,7 +84,9 @@ const char* hbg_ctx_last_kernel(const hbg_ctx* ctx);
  * 1 = dot products, 2 = butterflies, 3 = butterflies through the generic
  * shared-memory kernel even where a register-resident kernel exists (n = 16),
  * 4 = butterflies, n = 16 through the 8-values-in-registers split kernel even
- * where the 4-point-group kernel (d <= 8, the default) applies. */
+ * where the 4-point-group kernel (d <= 8, the default) applies, 5 = butterflies,
+ * n = 16 and d <= 8 through the load-balanced form of the 4-point-group kernel
+ * (the two threads of a polynomial hand two values over through shared memory). */
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path);
 /* Which dot-product kernel applies a matrix to the batch (results are
  * bit-identical): 0 = pick by size (default), 1 = matrix read through L1 from

@@ -65,7 +65,7 @@ def test_errors(ntl):
 
 
 def test_golden(ntl, golden):
-    for path in ("auto", "matrix", "ntt", "ntt-smem", "ntt-split"):
+    for path in ("auto", "matrix", "ntt", "ntt-smem", "ntt-split", "ntt-bal"):
         ntl._ctx(P).set_fft_path(path)
         kats.check_golden(ntl, golden)
     ntl._ctx(P).set_fft_path("auto")
@@ -125,7 +125,7 @@ def test_fft_vs_oracle(ntl, r, d, k, batch):
     omega = ROOTS_OF_UNITY[r] if r < len(ROOTS_OF_UNITY) else pow(7, (P - 1) // n, P)
     polys = [[rng.randrange(P) for _ in range(d)] for _ in range(batch)]
     want = orc.fft_batch_evaluate(polys, omega, P, n, k)
-    for path in ("matrix", "ntt", "ntt-smem", "ntt-split"):
+    for path in ("matrix", "ntt", "ntt-smem", "ntt-split", "ntt-bal"):
         if path == "matrix" and k * min(d, n) > 2 ** 18:
             continue
         ntl._ctx(P).set_fft_path(path)
@@ -150,7 +150,7 @@ def test_fft_small_prime(ntl):
         for d in (1, 4, 5, 6, 8, 13):
             polys = [[rng.randrange(p) for _ in range(d)] for _ in range(70)] + [[p - 1] * d]
             want = orc.fft_batch_evaluate(polys, w, p, 16, 16)
-            for path in ("ntt", "ntt-split", "ntt-smem", "matrix"):
+            for path in ("ntt", "ntt-split", "ntt-bal", "ntt-smem", "matrix"):
                 ntl._ctx(p).set_fft_path(path)
                 assert ntl.fft_batch_evaluate(polys, w, p, 16, 16) == want, (p, d, path)
             ntl._ctx(p).set_fft_path("auto")
