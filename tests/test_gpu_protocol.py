@@ -271,3 +271,93 @@ def test_robust_reconstruct_single_share(rs, omega):
 
     poly, errors = run(go())
     assert poly == coeffs and errors == {5}
+
+
+# --- n parties on n GPUs (party_sim.py): the CUDA codec, all parties in one process ---
+
+
+def _party_shares(n, t, batch, omega, seed):
+    import numpy as np
+    import torch
+
+    rng = random.Random(seed)
+    pt = _point(n, omega)
+    xs = [pt(i).value for i in range(n)]
+    secrets = [rng.randrange(P) for _ in range(batch)]
+    polys = [[s] + [rng.randrange(P) for _ in range(t)] for s in secrets]
+    out = []
+    for x in xs:
+        vals = [sum(c * pow(x, e, P) for e, c in enumerate(f)) % P for f in polys]
+        raw = b"".join(v.to_bytes(32, "little") for v in vals)
+        out.append(torch.from_numpy(np.frombuffer(raw, dtype=np.int64).reshape(batch, 4).copy()).cuda())
+    return secrets, out
+
+
+def _limbs_to_ints(t):
+    raw = t.cpu().contiguous().numpy().tobytes()
+    return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
+
+
+@pytest.mark.parametrize("n,t,batch,omega", [(4, 1, 256, False), (4, 1, 7, True), (16, 5, 1000, False),
+                                              (16, 5, 65, True), (7, 2, 33, False), (2, 0, 5, False)])
+def test_party_simulation_in_process(n, t, batch, omega):
+    import torch
+
+    from honeybadgermpc_b200 import party_sim
+
+    secrets, shares = _party_shares(n, t, batch, omega, seed=n * 1000 + batch)
+    codecs = [party_sim.CudaCodec(P, n, use_omega_powers=omega)] * n  # one GPU plays every party
+    for got, ok in party_sim.simulate_in_process(codecs, shares, t):
+        assert ok and _limbs_to_ints(got) == secrets
+    # a wrong share of the last party is noticed by everyone (re-encode + compare)
+    if n > t + 1:
+        shares[n - 1] = shares[n - 1].clone()
+        shares[n - 1][0, 0] += 1
+        res = party_sim.simulate_in_process(codecs, shares, t)
+        assert not any(ok for _, ok in res)
+    torch.cuda.synchronize()
+
+
+def _party_rank(rank, world, port, t, batch, results):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from honeybadgermpc_b200 import party_sim
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        secrets, shares = _party_shares(world, t, batch, False, seed=world + batch)
+        got, ok = party_sim.batch_reconstruct_collective(shares[rank], t, party_sim.CudaCodec(P, world))
+        results[rank] = bool(ok) and _limbs_to_ints(got) == secrets
+    finally:
+        dist.destroy_process_group()
+
+
+def test_party_simulation_nccl():
+    """one party per GPU over NCCL (needs >= 2 GPUs; the round-end single-GPU run skips it)"""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    t = (world - 1) // 3
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    results = ctx.Manager().dict()
+    procs = [ctx.Process(target=_party_rank, args=(r, world, port, t, 1000, results)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert dict(results) == {r: True for r in range(world)}
