@@ -1,8 +1,6 @@
 """The C++ CPU restatement (oracle/cpu_ref.cpp: checker #2 and the timed CPU
 baseline) against the Python oracle and the reference's known answers."""
 
-import ctypes
-import os
 import random
 import sys
 

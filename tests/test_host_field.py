@@ -4,7 +4,6 @@ the kernels run (even/odd CIOS multiplier, the BLS fast reduction rows, the
 lazy dot-product accumulator), checked against Python ints."""
 
 import ctypes
-import os
 import random
 import sys
 

@@ -1,7 +1,7 @@
 """kernel time vs batch size for the two cfg2 kernels (device-resident, CUDA events)"""
 import sys
 sys.path.insert(0, '.')
-import numpy as np, torch
+import torch
 from honeybadgermpc_b200 import _native, ntl
 from honeybadgermpc_b200.field import GF
 from honeybadgermpc_b200.polynomial import EvalPoint
