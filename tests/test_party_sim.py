@@ -103,6 +103,35 @@ def test_parties_as_ranks_gloo(world, t, batch, corrupt):
         assert all(match and ok for match, ok in res.values())
 
 
+class OracleOmegaCodec:
+    """omega-power points (FFT encode / interpolate of the oracle)"""
+
+    def __init__(self, p, n):
+        self.p, self.n = p, n
+        self.pt = orc.EvalPoint(p, n, True)
+
+    def encode(self, coeffs):
+        return to_limbs(orc.fft_batch_evaluate(to_ints(coeffs), self.pt.omega, self.p, self.pt.order, self.n))
+
+    def interpolate(self, z, ys):
+        return to_limbs(orc.fft_batch_interpolate(list(z), to_ints(ys), self.pt.omega, self.p, self.pt.order))
+
+
+@pytest.mark.parametrize("n,t,batch", [(16, 5, 20), (7, 2, 5)])
+def test_in_process_simulation_omega_points(n, t, batch):
+    rng = random.Random(n)
+    codec = OracleOmegaCodec(P, n)
+    xs = [codec.pt(i) for i in range(n)]
+    secrets = [rng.randrange(P) for _ in range(batch)]
+    polys = [[s] + [rng.randrange(P) for _ in range(t)] for s in secrets]
+    per_party = [to_limbs([[sum(c * pow(x, e, P) for e, c in enumerate(f)) % P] for f in polys]).reshape(batch, 4)
+                 for x in xs]
+    for got, ok in party_sim.simulate_in_process([codec] * n, per_party, t):
+        assert ok and [r[0] for r in to_ints(got.reshape(batch, 1, 4))] == secrets
+    per_party[n - 1][0, 0] += 1
+    assert not any(ok for _, ok in party_sim.simulate_in_process([codec] * n, per_party, t))
+
+
 def test_in_process_simulation_matches():
     n, t, batch = 4, 1, 9
     secrets, shares = make_shares(n, t, batch, seed=3)
