@@ -19,11 +19,13 @@ import logging
 import random
 import time
 
+import numpy as np
+
 from . import reed_solomon as rs
 from .field import GF
-from .ntl import pack_rows
+from .ntl import pack_rows, unpack_rows, wrap_elements
 from .polynomial import EvalPoint
-from .utils import chunk_data, flatten_lists, subscribe_recv, transpose_lists
+from .utils import chunk_data, subscribe_recv, transpose_lists
 
 ROUNDS = ("R1", "R2")
 
@@ -41,15 +43,18 @@ async def fetch_one(awaitables):
             yield position[task], await task
 
 
-async def incremental_decode(receivers, encoder, decoder, robust_decoder, batch_size, t, degree, n):
+async def incremental_decode(receivers, encoder, decoder, robust_decoder, batch_size, t, degree, n,
+                             limbs=False):
     """Feed columns to an ``IncrementalDecoder`` in arrival order until it is
-    done (batch_reconstruction.py:43-61); ``None`` if the senders run out."""
+    done (batch_reconstruction.py:43-61); ``None`` if the senders run out.
+    ``limbs=True`` returns the rows as ``uint64[batch, degree+1, 4]`` instead of
+    lists of ints (on the optimistic path no Python int is ever created)."""
     state = rs.IncrementalDecoder(encoder, decoder, robust_decoder, degree=degree,
                                   batch_size=batch_size, max_errors=t)
     async for sender, column in fetch_one(receivers):
         state.add(sender, column)
         if state.done():
-            rows, _ = state.get_results()
+            rows, _ = state.get_results_limbs() if limbs else state.get_results()
             return rows
     return None
 
@@ -117,7 +122,8 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     async def decode_round(tag):
         started = time.time()
         try:
-            rows = await incremental_decode(inbox.columns[tag], *codec, len(chunks), t, k - 1, n)
+            rows = await incremental_decode(inbox.columns[tag], *codec, len(chunks), t, k - 1, n,
+                                            limbs=True)
         except asyncio.CancelledError:
             inbox.close()
             raise
@@ -144,8 +150,8 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
 
     # R2: broadcast the constant terms = the chunk polynomials G_c at my point
     started = time.time()
-    constants = [row[0] for row in mine]
-    payload = pack_rows([constants], len(chunks), p)[0].tobytes() if wire == "limbs" else constants
+    constants = np.ascontiguousarray(mine[:, :1, :])  # uint64[chunks, 1, 4]
+    payload = constants.tobytes() if wire == "limbs" else [row[0] for row in unpack_rows(constants)]
     for j in range(n):
         send(j, ("R2", payload))
     timing.info("[BatchReconstruct] P2 Send: %s", time.time() - started)
@@ -154,6 +160,6 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
         return None
 
     inbox.close()
-    opened = flatten_lists(secrets)
-    assert len(opened) >= len(values)
-    return field.wrap_canonical(opened[: len(values)])
+    opened = secrets.reshape(-1, 4)  # uint64[chunks * k, 4]: the coefficient rows, flattened
+    assert opened.shape[0] >= len(values)
+    return wrap_elements(opened[: len(values)], field)

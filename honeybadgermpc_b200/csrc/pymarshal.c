@@ -9,6 +9,7 @@
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <string.h>
+#include <structmember.h>
 
 static int ge_le32(const unsigned char* a, const unsigned char* b) {
   for (int i = 31; i >= 0; i--) {
@@ -95,4 +96,52 @@ PyObject* hbg_py_unpack_rows(const unsigned char* in, Py_ssize_t batch, Py_ssize
     PyList_SET_ITEM(outer, i, row);
   }
   return outer;
+}
+
+/* Offset of a __slots__ member of a class, or -1 with an exception set. */
+static Py_ssize_t slot_offset(PyObject* cls, const char* name) {
+  PyObject* d = PyObject_GetAttrString(cls, name);
+  if (!d) return -1;
+  if (Py_TYPE(d) != &PyMemberDescr_Type || ((PyMemberDescrObject*)d)->d_member->type != T_OBJECT_EX) {
+    Py_DECREF(d);
+    PyErr_Format(PyExc_TypeError, "%s is not a __slots__ member", name);
+    return -1;
+  }
+  Py_ssize_t off = ((PyMemberDescrObject*)d)->d_member->offset;
+  Py_DECREF(d);
+  return off;
+}
+
+/* in[count][32] (canonical residues) -> list of `count` instances of `cls`, a class with the
+ * slots (value, field, modulus) -- GFElement -- built without running its __init__:
+ * value = the int, field / modulus = the given objects.  What batch_reconstruct returns;
+ * in Python this loop is the largest single cost of a big open once the kernels are fast. */
+PyObject* hbg_py_wrap_elements(const unsigned char* in, Py_ssize_t count, PyObject* cls, PyObject* field,
+                               PyObject* modulus) {
+  if (!PyType_Check(cls)) {
+    PyErr_SetString(PyExc_TypeError, "cls must be a class");
+    return NULL;
+  }
+  PyTypeObject* tp = (PyTypeObject*)cls;
+  const Py_ssize_t ov = slot_offset(cls, "value"), of = slot_offset(cls, "field"),
+                   om = slot_offset(cls, "modulus");
+  if (ov < 0 || of < 0 || om < 0) return NULL;
+  PyObject* out = PyList_New(count);
+  if (!out) return NULL;
+  for (Py_ssize_t i = 0; i < count; i++) {
+    PyObject* v = _PyLong_FromByteArray(in + (size_t)i * 32, 32, 1, 0);
+    PyObject* e = v ? tp->tp_alloc(tp, 0) : NULL;
+    if (!e) {
+      Py_XDECREF(v);
+      Py_DECREF(out);
+      return NULL;
+    }
+    *(PyObject**)((char*)e + ov) = v;  /* steals the reference */
+    Py_INCREF(field);
+    *(PyObject**)((char*)e + of) = field;
+    Py_INCREF(modulus);
+    *(PyObject**)((char*)e + om) = modulus;
+    PyList_SET_ITEM(out, i, e);
+  }
+  return out;
 }

@@ -110,6 +110,9 @@ def _load_marshal():
                                          ctypes.c_void_p]
         lib.hbg_py_unpack_rows.restype = ctypes.py_object
         lib.hbg_py_unpack_rows.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_ssize_t]
+        lib.hbg_py_wrap_elements.restype = ctypes.py_object
+        lib.hbg_py_wrap_elements.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.py_object,
+                                             ctypes.py_object, ctypes.py_object]
         return lib
     except (OSError, AttributeError):
         return None
@@ -139,6 +142,17 @@ def unpack_rows(arr):
         return _unpack_rows_py(arr)
     arr = np.ascontiguousarray(arr)
     return _marshal.hbg_py_unpack_rows(arr.ctypes.data, arr.shape[0], arr.shape[1])
+
+
+def wrap_elements(arr, field):
+    """uint64[count, 4] canonical residues -> list of ``GFElement`` of ``field`` (what
+    ``batch_reconstruct`` returns), built in C without a Python-level loop."""
+    from ..field import GFElement
+
+    arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    if _marshal is None:
+        return field.wrap_canonical(unpack_rows(arr[None])[0]) if arr.shape[0] else []
+    return _marshal.hbg_py_wrap_elements(arr.ctypes.data, arr.shape[0], GFElement, field, field.modulus)
 
 
 def _strip(a):

@@ -241,6 +241,9 @@ class WelchBerlekampRobustDecoder(RobustDecoder):
         return out
 
 
+_GUESS = object()  # IncrementalDecoder._result: "the accepted optimistic guess, still as limbs"
+
+
 class IncrementalDecoder:
     """reed_solomon.py:232-403.  Feed it one party's column at a time with
     ``add(idx, data)``; it decodes optimistically from the first degree+1
@@ -310,7 +313,7 @@ class IncrementalDecoder:
             self._optimistic = False
             return False
         if len(self._z) >= self._need():
-            self._result = unpack_rows(self._guess)
+            self._result = _GUESS  # the int rows are made on demand (get_results)
             self._result_is_guess = True
         return True
 
@@ -360,6 +363,8 @@ class IncrementalDecoder:
     def get_results(self):
         if self._result is None:
             return None, None
+        if self._result is _GUESS:
+            self._result = unpack_rows(self._guess)
         return self._result, self._confirmed_errors
 
     def get_results_limbs(self):
@@ -367,7 +372,7 @@ class IncrementalDecoder:
         if self._result is None:
             return None, None
         if self._guess is not None and self._result_is_guess:
-            return self._guess, self._confirmed_errors
+            return self._guess, self._confirmed_errors  # no Python ints were ever made
         return pack_rows(self._result, self.degree + 1, self.modulus), self._confirmed_errors
 
 
