@@ -109,3 +109,38 @@ def test_host_marshalling_round_trip():
     assert unpack_rows(arr) == [[0, 1, P - 1], [0, 5, 0], [0, 0, 0]]
     with pytest.raises(OverflowError):
         pack_rows([[-1]], 1, P)
+
+
+def test_c_element_wrapping_matches_python():
+    """hbg_py_wrap_elements (csrc/pymarshal.c) builds the same GFElement objects as the
+    Python constructor; the pure-Python fallback of ntl.wrap_elements agrees"""
+    import gc
+    import random
+
+    import numpy as np
+
+    graft.build_marshal()
+    import importlib
+
+    import honeybadgermpc_b200.ntl as ntl
+    from honeybadgermpc_b200.field import GF, GFElement
+
+    ntl = importlib.reload(ntl)
+    assert ntl._marshal is not None
+    field = GF(P)
+    rng = random.Random(9)
+    vals = [0, 1, P - 1, 2 ** 64, 2 ** 255 % P] + [rng.randrange(P) for _ in range(500)]
+    arr = ntl.pack_rows([vals], len(vals), P)[0]
+    got = ntl.wrap_elements(arr, field)
+    assert [type(e) for e in got] == [GFElement] * len(vals)
+    assert got == [field(v) for v in vals]
+    assert all(e.field is field and e.modulus == P and e.value == v for e, v in zip(got, vals))
+    assert (got[3] * got[4] + 1).value == (vals[3] * vals[4] + 1) % P  # usable like any other element
+    assert ntl.wrap_elements(np.zeros((0, 4), np.uint64), field) == []
+    saved, ntl._marshal = ntl._marshal, None
+    try:
+        assert ntl.wrap_elements(arr, field) == got
+    finally:
+        ntl._marshal = saved
+    del got
+    gc.collect()
