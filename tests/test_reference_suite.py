@@ -1,5 +1,5 @@
-"""Run the reference's OWN test files, unchanged, with the oracle standing in
-for the compiled NTL extension.  Only possible where /root/reference exists
+"""Run the reference's OWN test files, unchanged, with the oracle -- or our shim
+on top of the oracle -- standing in for the compiled NTL extension.  Only possible where /root/reference exists
 (the authoring container); skipped elsewhere.  This is the strongest pin on
 the oracle short of NTL itself: the reference's encoders, decoders,
 IncrementalDecoder, batch_reconstruct, randousha and refinement programs all
@@ -34,11 +34,17 @@ DESELECT = ["rust", "reconstruction_timeout"]
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
-def test_reference_tests_pass_on_oracle():
+@pytest.mark.parametrize("impl", ["oracle", "b200-host"])
+def test_reference_tests_pass(impl):
+    """impl = "oracle": the oracle module stands in for the NTL extension (pins the oracle).
+    impl = "b200-host": OUR ctypes shim (honeybadgermpc_b200.ntl) stands in for it, with the
+    oracle behind the native Context interface instead of the CUDA library -- the drop-in
+    boundary of INTEGRATION.md exercised by the reference's own callers and tests, on CPU
+    (argument conventions, shapes, padding / truncation, error behaviour of the shim)."""
     with tempfile.TemporaryDirectory() as tmp:
         with open(os.path.join(tmp, "pytest.ini"), "w") as fh:
             fh.write("[pytest]\n")
-        env = dict(os.environ, PYTHONPATH=os.path.join(HERE, "golden"), HBMPC_NTL_IMPL="oracle")
+        env = dict(os.environ, PYTHONPATH=os.path.join(HERE, "golden"), HBMPC_NTL_IMPL=impl)
         cmd = [sys.executable, "-m", "pytest", "-c", os.path.join(tmp, "pytest.ini"),
                "--rootdir", tmp, "-p", "ref_plugin", "-p", "no:cacheprovider", "-q",
                "-k", " and ".join(f"not {d}" for d in DESELECT)]
