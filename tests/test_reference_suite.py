@@ -53,3 +53,30 @@ def test_reference_tests_pass(impl):
         tail = res.stdout[-2000:] + res.stderr[-2000:]
         assert res.returncode == 0, tail
         assert " passed" in res.stdout and "failed" not in res.stdout.splitlines()[-1], tail
+
+
+# the reference's tests of the path's classes, run against OUR mirror modules (field, reed_solomon,
+# batch_reconstruction, robust_reconstruction injected in place of the reference's)
+MIRROR_FILES = [
+    "tests/test_reed_solomon.py",
+    "tests/test_batch_reconstruction.py",
+    "tests/test_polynomial.py",
+    "tests/progs/test_random_refinement.py",
+    "tests/progs/test_triple_refinement.py",
+]
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_reference_tests_pass_on_our_mirror_modules():
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "pytest.ini"), "w") as fh:
+            fh.write("[pytest]\n")
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(HERE, "golden"), HERE]))
+        cmd = [sys.executable, "-m", "pytest", "-c", os.path.join(tmp, "pytest.ini"),
+               "--rootdir", tmp, "-p", "ref_plugin_mirror", "-p", "no:cacheprovider", "-q",
+               "--timeout", "120", "-k", " and ".join(f"not {d}" for d in DESELECT)]
+        cmd += [os.path.join(ref_shim.REFERENCE_ROOT, f) for f in MIRROR_FILES]
+        res = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
+        tail = res.stdout[-2000:] + res.stderr[-2000:]
+        assert res.returncode == 0, tail
+        assert " passed" in res.stdout and "failed" not in res.stdout.splitlines()[-1], tail
