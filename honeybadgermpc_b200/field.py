@@ -43,6 +43,33 @@ def is_probable_prime(n):
     return True
 
 
+def sqrt_mod_prime(a, p):
+    """A square root of ``a`` modulo the odd prime ``p`` (Tonelli-Shanks on Python ints; the
+    smaller of the two roots).  Raises ``ValueError`` for a non-residue."""
+    a %= p
+    if a == 0:
+        return 0
+    if pow(a, (p - 1) // 2, p) != 1:
+        raise ValueError("not a quadratic residue")
+    q, s = p - 1, 0
+    while q % 2 == 0:
+        q //= 2
+        s += 1
+    g = 2
+    while pow(g, (p - 1) // 2, p) != p - 1:
+        g += 1
+    m, c, t, r = s, pow(g, q, p), pow(a, q, p), pow(a, (q + 1) // 2, p)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % p
+            i += 1
+        b = pow(c, 1 << (m - i - 1), p)
+        m, c = i, b * b % p
+        t, r = t * c % p, r * b % p
+    return min(r, p - r)
+
+
 class GF:
     """One object per modulus (field.py:41-58)."""
 
@@ -136,6 +163,12 @@ class GFElement:
         if self.value == 0:
             raise ZeroDivisionError("inverse of 0")
         return GFElement(pow(self.value, -1, self.modulus), self.field)
+
+    def sqrt(self):
+        """field.py:170-208: a square root (either one; the offline bit generation only needs
+        every party to take the same root of the same public value)."""
+        assert self.modulus % 2 == 1, "Modulus must be odd"
+        return GFElement(sqrt_mod_prime(self.value, self.modulus), self.field)
 
     def __truediv__(self, other):
         v = self._coerce(other)

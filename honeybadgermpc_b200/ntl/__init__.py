@@ -350,25 +350,9 @@ def sqrt_mod(a, n):
     a = _to_int(a) % p
     if a == 0 or p == 2:
         return a
-    if pow(a, (p - 1) // 2, p) != 1:
-        raise ValueError("not a quadratic residue")
-    q, s = p - 1, 0
-    while q % 2 == 0:
-        q //= 2
-        s += 1
-    g = 2
-    while pow(g, (p - 1) // 2, p) != p - 1:
-        g += 1
-    m, c, t, r = s, pow(g, q, p), pow(a, q, p), pow(a, (q + 1) // 2, p)
-    while t != 1:
-        i, t2 = 0, t
-        while t2 != 1:
-            t2 = t2 * t2 % p
-            i += 1
-        b = pow(c, 1 << (m - i - 1), p)
-        m, c = i, b * b % p
-        t, r = t * c % p, r * b % p
-    return min(r, p - r)
+    from ..field import sqrt_mod_prime
+
+    return sqrt_mod_prime(a, p)
 
 
 # thread knobs: the GPU path has no thread pool; the values are stored and

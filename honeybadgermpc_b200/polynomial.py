@@ -53,3 +53,34 @@ class EvalPoint:
 
     def zero(self):
         return self.field(0)
+
+
+class OpenedPolynomial(list):
+    """What ``robust_reconstruct`` returns: the coefficients of the opened polynomial (a
+    ``list`` of ints, lowest degree first) that can also be called like the reference's
+    ``polynomials_over(field)(coeffs)`` object -- ``Mpc.open_share`` evaluates it at zero
+    (mpc.py:157).  ``coeffs``: the coefficients as field elements, trailing zeros stripped
+    (polynomial.py:36).  Not the reference's general ``Polynomial`` class (arithmetic,
+    interpolation: outside this path)."""
+
+    def __init__(self, coeffs, field):
+        super().__init__(int(c) for c in coeffs)
+        self.field = field
+
+    @property
+    def coeffs(self):
+        vals = list(self)
+        while vals and vals[-1] == 0:
+            vals.pop()
+        return [self.field(v) for v in vals]
+
+    def degree(self):
+        return max(len(self.coeffs) - 1, 0)
+
+    def __call__(self, x):
+        p = self.field.modulus
+        xv = int(x) % p
+        acc = 0
+        for c in reversed(self):
+            acc = (acc * xv + c) % p
+        return self.field(acc)

@@ -5,6 +5,7 @@ incremental decoder with a batch of one, so it runs the same kernels as
 
 from . import reed_solomon as rs
 from .batch_reconstruction import fetch_one
+from .polynomial import OpenedPolynomial
 
 
 def _codec_for(point, t):
@@ -15,14 +16,14 @@ def _codec_for(point, t):
 
 async def robust_reconstruct(field_futures, field, n, t, point, degree):
     """``field_futures[i]`` resolves to party i's share (a ``GFElement``).
-    Returns ``(coefficients of the opened polynomial, error parties)``; the
-    reference wraps the coefficients in its pure-Python ``Polynomial`` class,
-    which is outside this path.  ``(None, None)`` if too few shares arrive."""
+    Returns ``(opened polynomial, error parties)``: the polynomial is the list of its
+    coefficients and is callable like the reference's ``Polynomial`` object
+    (``Mpc.open_share`` evaluates it at zero).  ``(None, None)`` if too few shares arrive."""
     state = rs.IncrementalDecoder(*_codec_for(point, t), degree, 1, t)
     async for party, share in fetch_one(field_futures):
         state.add(party, [share.value])
         if not state.done():
             continue
         rows, errors = state.get_results()
-        return rows[0], errors
+        return OpenedPolynomial(rows[0], field), errors
     return None, None

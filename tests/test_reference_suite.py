@@ -57,13 +57,7 @@ def test_reference_tests_pass(impl):
 
 # the reference's tests of the path's classes, run against OUR mirror modules (field, reed_solomon,
 # batch_reconstruction, robust_reconstruction injected in place of the reference's)
-MIRROR_FILES = [
-    "tests/test_reed_solomon.py",
-    "tests/test_batch_reconstruction.py",
-    "tests/test_polynomial.py",
-    "tests/progs/test_random_refinement.py",
-    "tests/progs/test_triple_refinement.py",
-]
+MIRROR_FILES = FILES  # all nine: Mpc.open / ShareArray.open, randousha and the refinement programs included
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
