@@ -39,6 +39,8 @@ def test_ntl_shim_kats(ntl):
     kats.check_fft_interpolate(ntl)
     kats.check_threads(ntl)
     kats.check_errors(ntl)
+    kats.check_sqrt(ntl)
+    kats.check_fft_properties(ntl)
 
 
 def test_encoder_decoder_kats(rs):
@@ -73,3 +75,19 @@ def test_batch_reconstruct_random(rs, n, t, count, omega, algo):
 @pytest.mark.parametrize("omega", [False, True])
 def test_robust_reconstruct_single_share(rs, omega):
     gp.test_robust_reconstruct_single_share(rs, omega)
+
+
+def test_opened_polynomial_and_sqrt():
+    from honeybadgermpc_b200.field import GF
+    from honeybadgermpc_b200.polynomial import OpenedPolynomial
+
+    f = GF(P)
+    poly = OpenedPolynomial([5, 0, 7, 0], f)
+    assert poly == [5, 0, 7, 0] and poly.coeffs == [f(5), f(0), f(7)] and poly.degree() == 2
+    assert poly(f(0)) == 5 and poly(3) == 5 + 7 * 9 and type(poly(f(2))).__name__ == "GFElement"
+    assert OpenedPolynomial([], f)(f(4)) == 0
+    for v in (4, 9, 1234567 ** 2):
+        r = f(v).sqrt()
+        assert r * r == v
+    with pytest.raises(ValueError):
+        GF(13)(2).sqrt()  # 2 is not a square mod 13
