@@ -164,10 +164,14 @@ class GFElement:
             raise ZeroDivisionError("inverse of 0")
         return GFElement(pow(self.value, -1, self.modulus), self.field)
 
+    __invert__ = inverse  # the reference spells the inverse ~x (field.py:126-150)
+
     def sqrt(self):
         """field.py:170-208: a square root (either one; the offline bit generation only needs
-        every party to take the same root of the same public value)."""
+        every party to take the same root of the same public value).  A non-residue fails the
+        reference's assertion."""
         assert self.modulus % 2 == 1, "Modulus must be odd"
+        assert pow(self.value, (self.modulus - 1) // 2, self.modulus) in (0, 1)
         return GFElement(sqrt_mod_prime(self.value, self.modulus), self.field)
 
     def __truediv__(self, other):
@@ -176,15 +180,34 @@ class GFElement:
             return NotImplemented
         return self * GFElement(v, self.field).inverse()
 
+    __floordiv__ = __truediv__  # field.py:151-162: every division is the field division
+
     def __rtruediv__(self, other):
         return GFElement(other, self.field) * self.inverse()
 
+    __rfloordiv__ = __rtruediv__
+
+    def bit(self, index):
+        return (self.value >> index) & 1
+
+    def signed(self):
+        """value, or value - p when it is above (p - 1) / 2 (field.py:214-222)"""
+        return self.value - self.modulus if 2 * self.value > self.modulus - 1 else self.value
+
+    def unsigned(self):
+        return self.value
+
     def __eq__(self, other):
+        # field.py:239-246: elements of different fields do not compare (FieldsNotIdentical);
+        # anything else is compared with the raw value
         if isinstance(other, GFElement):
-            return self.field is other.field and self.value == other.value
-        if isinstance(other, int):
-            return self.value == other % self.modulus
-        return NotImplemented
+            if other.field is not self.field:
+                raise FieldsNotIdentical
+            return self.value == other.value
+        return self.value == other
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
 
     def __hash__(self):
         return hash((self.value, self.modulus))
@@ -194,3 +217,5 @@ class GFElement:
 
     def __repr__(self):
         return "{%d}" % self.value
+
+    __str__ = __repr__

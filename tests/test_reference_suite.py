@@ -57,7 +57,9 @@ def test_reference_tests_pass(impl):
 
 # the reference's tests of the path's classes, run against OUR mirror modules (field, reed_solomon,
 # batch_reconstruction, robust_reconstruction injected in place of the reference's)
-MIRROR_FILES = FILES  # all nine: Mpc.open / ShareArray.open, randousha and the refinement programs included
+# all nine (Mpc.open / ShareArray.open, randousha and the refinement programs included), plus the
+# reference's tests of the field class and of the preprocessing files written through the encoders
+MIRROR_FILES = FILES + ["tests/test_field.py", "tests/test_preprocessing.py"]
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
