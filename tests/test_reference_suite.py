@@ -59,7 +59,8 @@ def test_reference_tests_pass(impl):
 # batch_reconstruction, robust_reconstruction injected in place of the reference's)
 # all nine (Mpc.open / ShareArray.open, randousha and the refinement programs included), plus the
 # reference's tests of the field class and of the preprocessing files written through the encoders
-MIRROR_FILES = FILES + ["tests/test_field.py", "tests/test_preprocessing.py"]
+MIRROR_FILES = FILES + ["tests/test_field.py", "tests/test_preprocessing.py",
+                        "tests/progs/mixins/test_share_arithmetic.py"]
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
