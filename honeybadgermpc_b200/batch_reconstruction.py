@@ -25,7 +25,7 @@ from . import reed_solomon as rs
 from .field import GF
 from .ntl import pack_rows, unpack_rows, wrap_elements
 from .polynomial import EvalPoint
-from .utils import chunk_data, subscribe_recv, transpose_lists
+from .utils import chunk_data, gc_paused, subscribe_recv, transpose_lists
 
 ROUNDS = ("R1", "R2")
 
@@ -105,7 +105,8 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     of a pickled int list.  All parties of a run must use the same format."""
     timing = logging.LoggerAdapter(logging.getLogger("benchmark_logger"), {"node_id": myid})
     k = (t if degree is None else degree) + 1
-    values = [share.value for share in secret_shares]
+    with gc_paused():
+        values = [share.value for share in secret_shares]
     if config is not None and config.induce_faults:  # fault injection hook of the reference (:129-131)
         logging.debug("[FAULT][BatchReconstruction] Sending random shares.")
         values = [random.randint(0, p - 1) for _ in values]
@@ -117,7 +118,8 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     codec = (rs.EncoderFactory.get(point, kind), rs.DecoderFactory.get(point, kind),
              rs.RobustDecoderFactory.get(
                  t, point, algorithm=rs.Algorithm.GAO if config is None else config.decoding_algorithm))
-    chunks = chunk_data(values, k)
+    with gc_paused():
+        chunks = chunk_data(values, k)
 
     async def decode_round(tag):
         started = time.time()
@@ -136,11 +138,12 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
 
     # R1: party j receives the j-th evaluation of every chunk polynomial
     started = time.time()
-    if wire == "limbs":
-        encoded = codec[0].encode_batch_limbs(pack_rows(chunks, k, p))  # [chunks][n][4]
-        outgoing = [encoded[:, j, :].tobytes() for j in range(n)]
-    else:
-        outgoing = transpose_lists(codec[0].encode(chunks))
+    with gc_paused():
+        if wire == "limbs":
+            encoded = codec[0].encode_batch_limbs(pack_rows(chunks, k, p))  # [chunks][n][4]
+            outgoing = [encoded[:, j, :].tobytes() for j in range(n)]
+        else:
+            outgoing = transpose_lists(codec[0].encode(chunks))
     for j, column in enumerate(outgoing):
         send(j, ("R1", column))
     timing.info("[BatchReconstruct] P1 Send: %s", time.time() - started)
@@ -151,7 +154,8 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     # R2: broadcast the constant terms = the chunk polynomials G_c at my point
     started = time.time()
     constants = np.ascontiguousarray(mine[:, :1, :])  # uint64[chunks, 1, 4]
-    payload = constants.tobytes() if wire == "limbs" else [row[0] for row in unpack_rows(constants)]
+    with gc_paused():
+        payload = constants.tobytes() if wire == "limbs" else [row[0] for row in unpack_rows(constants)]
     for j in range(n):
         send(j, ("R2", payload))
     timing.info("[BatchReconstruct] P2 Send: %s", time.time() - started)
@@ -162,4 +166,5 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     inbox.close()
     opened = secrets.reshape(-1, 4)  # uint64[chunks * k, 4]: the coefficient rows, flattened
     assert opened.shape[0] >= len(values)
-    return wrap_elements(opened[: len(values)], field)
+    with gc_paused():
+        return wrap_elements(opened[: len(values)], field)

@@ -136,6 +136,12 @@ PyObject* hbg_py_wrap_elements(const unsigned char* in, Py_ssize_t count, PyObje
       Py_DECREF(out);
       return NULL;
     }
+    /* An element refers to an int and to its (immortal, per-modulus) field object: it can never
+     * be part of a reference cycle, so it does not need to be tracked by the cyclic GC -- and
+     * hundreds of thousands of tracked elements make every full collection of the process
+     * slower (measured: a 49 152-share open spent more time in collections triggered by its own
+     * bulk allocations than in anything else). */
+    PyObject_GC_UnTrack(e);
     *(PyObject**)((char*)e + ov) = v;  /* steals the reference */
     Py_INCREF(field);
     *(PyObject**)((char*)e + of) = field;

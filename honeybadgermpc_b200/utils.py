@@ -3,7 +3,28 @@
 ``@TypeCheck`` decorators of the reference are not reproduced."""
 
 import asyncio
+import contextlib
+import gc
 from collections import defaultdict
+
+
+@contextlib.contextmanager
+def gc_paused():
+    """Keep the cyclic garbage collector from running inside a bulk conversion.
+
+    Turning B limbs into B Python objects (or chunking B ints into lists) allocates tens of
+    thousands of container objects in one go; every 700 of them the collector starts a pass,
+    and its older generations walk every tracked object of the process.  None of the objects
+    made here can be part of a cycle.  Measured on a 49 152-share open at n = 16: collections
+    triggered by these conversions cost more than the conversions themselves.  Only used
+    around synchronous sections (no ``await`` inside)."""
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 def wrap_send(tag, send):
