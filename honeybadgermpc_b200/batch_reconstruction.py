@@ -25,7 +25,7 @@ from . import reed_solomon as rs
 from .field import GF
 from .ntl import pack_rows, unpack_rows, wrap_elements
 from .polynomial import EvalPoint
-from .utils import chunk_data, gc_paused, subscribe_recv, transpose_lists
+from .utils import gc_paused, subscribe_recv
 
 ROUNDS = ("R1", "R2")
 
@@ -118,13 +118,17 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     codec = (rs.EncoderFactory.get(point, kind), rs.DecoderFactory.get(point, kind),
              rs.RobustDecoderFactory.get(
                  t, point, algorithm=rs.Algorithm.GAO if config is None else config.decoding_algorithm))
-    with gc_paused():
-        chunks = chunk_data(values, k)
+    if not values:
+        # unreachable from Mpc (open_share_array returns early on empty arrays, mpc.py:175-177); the
+        # reference fails here too (chunk_data([]) gives a flat list, utils/misc.py:40-41)
+        inbox.close()
+        raise TypeError("batch_reconstruct needs at least one share")
+    n_chunks = -(-len(values) // k)  # chunk polynomials of k coefficients, the last zero padded
 
     async def decode_round(tag):
         started = time.time()
         try:
-            rows = await incremental_decode(inbox.columns[tag], *codec, len(chunks), t, k - 1, n,
+            rows = await incremental_decode(inbox.columns[tag], *codec, n_chunks, t, k - 1, n,
                                             limbs=True)
         except asyncio.CancelledError:
             inbox.close()
@@ -139,11 +143,13 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     # R1: party j receives the j-th evaluation of every chunk polynomial
     started = time.time()
     with gc_paused():
-        if wire == "limbs":
-            encoded = codec[0].encode_batch_limbs(pack_rows(chunks, k, p))  # [chunks][n][4]
-            outgoing = [encoded[:, j, :].tobytes() for j in range(n)]
-        else:
-            outgoing = transpose_lists(codec[0].encode(chunks))
+        # chunk_data + encode + transpose_lists of the reference (:158-167) on limb arrays: the flat
+        # share list is packed once (zero padded to n_chunks * k), reshaped into the chunk
+        # polynomials, encoded, and transposed per destination before any Python list is made
+        coeffs = pack_rows([values], n_chunks * k, p)[0].reshape(n_chunks, k, 4)
+        encoded = codec[0].encode_batch_limbs(coeffs)                        # [chunks][n][4]
+        by_dest = np.ascontiguousarray(encoded.transpose(1, 0, 2))           # [n][chunks][4]
+        outgoing = [by_dest[j].tobytes() for j in range(n)] if wire == "limbs" else unpack_rows(by_dest)
     for j, column in enumerate(outgoing):
         send(j, ("R1", column))
     timing.info("[BatchReconstruct] P1 Send: %s", time.time() - started)
