@@ -77,3 +77,23 @@ def test_reference_tests_pass_on_our_mirror_modules():
         tail = res.stdout[-2000:] + res.stderr[-2000:]
         assert res.returncode == 0, tail
         assert " passed" in res.stdout and "failed" not in res.stdout.splitlines()[-1], tail
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_reference_batch_opening_benchmark_logic_on_our_mirror():
+    """BASELINE.json configs[0]: the reference's benchmark/test_benchmark_batch_opening.py --
+    TaskProgramRunner, 4 parties in one process, ShareArray.open() of 256 random shares -- run
+    unchanged (once, not timed) on top of our mirror modules and shim."""
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "pytest.ini"), "w") as fh:
+            fh.write("[pytest]\n")
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join(
+            [os.path.join(HERE, "golden"), HERE, ref_shim.REFERENCE_ROOT]))
+        cmd = [sys.executable, "-m", "pytest", "-c", os.path.join(tmp, "pytest.ini"),
+               "--rootdir", tmp, "-p", "ref_plugin_bench", "-p", "no:cacheprovider", "-q",
+               "--timeout", "120", "-k", "4-1-256 or 4-1-8 or 7-2-64",
+               os.path.join(ref_shim.REFERENCE_ROOT, "benchmark/test_benchmark_batch_opening.py")]
+        res = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=600)
+        tail = res.stdout[-2000:] + res.stderr[-2000:]
+        assert res.returncode == 0, tail
+        assert "3 passed" in res.stdout, tail
