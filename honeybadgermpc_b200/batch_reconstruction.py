@@ -155,6 +155,7 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     timing.info("[BatchReconstruct] P1 Send: %s", time.time() - started)
     mine = await decode_round("R1")
     if mine is None:
+        inbox.close()
         return None
 
     # R2: broadcast the constant terms = the chunk polynomials G_c at my point
@@ -167,6 +168,7 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     timing.info("[BatchReconstruct] P2 Send: %s", time.time() - started)
     secrets = await decode_round("R2")
     if secrets is None:
+        inbox.close()
         return None
 
     inbox.close()

@@ -123,7 +123,22 @@ int ensure(hbg_ctx* ctx, DevBuf& b, size_t bytes) {
   return HBG_OK;
 }
 
-// Cached device constant; `build` fills the host bytes when the key is new.
+// The constant cache is bounded by dropping it wholesale -- but only at the ENTRY of a C-ABI
+// call (every batch entry point calls this before its first lookup), never from inside
+// get_const: a call may hold several cached pointers at once (Gao: the interpolation matrix
+// and g0), and kernels of earlier calls on this stream may still be reading theirs.
+int cache_trim(hbg_ctx* ctx) {
+  if (ctx->cache_bytes <= ((size_t)256 << 20)) return HBG_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& kv : ctx->cache) cudaFree(kv.second.p);
+  ctx->cache.clear();
+  ctx->host_cache.clear();
+  ctx->cache_bytes = 0;
+  return HBG_OK;
+}
+
+// Cached device constant; `build` fills the host bytes when the key is new (and may add the
+// key's host-side twin to host_cache: both maps are only ever cleared together, above).
 template <class Build>
 int get_const(hbg_ctx* ctx, const std::string& key, const void** out, Build build) {
   auto it = ctx->cache.find(key);
@@ -134,13 +149,6 @@ int get_const(hbg_ctx* ctx, const std::string& key, const void** out, Build buil
   std::vector<uint32_t> host;
   int rc = build(host);
   if (rc != HBG_OK) return rc;
-  if (ctx->cache_bytes > (256u << 20)) {  // bound the cache: drop everything
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (auto& kv : ctx->cache) cudaFree(kv.second.p);
-    ctx->cache.clear();
-    ctx->host_cache.clear();
-    ctx->cache_bytes = 0;
-  }
   DevConst dc;
   dc.bytes = host.size() * 4;
   CU(cudaMalloc(&dc.p, dc.bytes ? dc.bytes : 4));
@@ -618,6 +626,7 @@ int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const u
     return fail(ctx, HBG_ERR_INVALID, "loc_stride must be at least m - (m+k)/2 + 1");
   if (mem != HBG_MEM_HOST && mem != HBG_MEM_DEVICE) return fail(ctx, HBG_ERR_INVALID, "bad mem flag");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   // constants: V(x)^-1 scaled into "double Montgomery" form (so that the interpolants come
   // out of apply_matrix in Montgomery form) and g0 = prod (X - x_i)
   const void* d_m = nullptr;
@@ -722,6 +731,7 @@ int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_ma
   if (m < 1 || k < 1 || e_max < 1 || !xs) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
   if (mem != HBG_MEM_HOST && mem != HBG_MEM_DEVICE) return fail(ctx, HBG_ERR_INVALID, "bad mem flag");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   const int pw_stride = e_max + k;
   const void* d_pw = nullptr;
   int rc = get_const(ctx, make_key("wbpw", xs, (size_t)m * 32, nullptr, 0, m, pw_stride), &d_pw,
@@ -936,6 +946,7 @@ int hbg_vandermonde_batch_evaluate(hbg_ctx* ctx, const uint64_t* xs, int n, cons
   if (batch == 0 || n == 0) return HBG_OK;
   if (!out || (d && !polys)) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   const void* d_m = nullptr;
   int rc = get_const(ctx, make_key("vdm", xs, (size_t)n * 32, nullptr, 0, n, d), &d_m,
                      [&](std::vector<uint32_t>& host) {
@@ -965,6 +976,7 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
   if (!ctx) return HBG_ERR_INVALID;
   if (k < 0 || (k && !xs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   const void* d_m = nullptr;
   // the singularity check must run even for an empty batch (pyx:167-169)
   const std::string key = make_key("vinv", xs, (size_t)k * 32, nullptr, 0, k);
@@ -986,6 +998,7 @@ int hbg_allgather_block(hbg_ctx* ctx, const void* block, size_t bytes, void* con
     return fail(ctx, HBG_ERR_INVALID, "bad argument (sizes and offsets must be multiples of 16)");
   if (bytes == 0) return HBG_OK;
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   GatherDst g;
   memset(&g, 0, sizeof(g));
   g.world = world;
@@ -1013,6 +1026,7 @@ int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], i
     return fail(ctx, HBG_ERR_INVALID, "bad argument");
   if (k > 8) return fail(ctx, HBG_ERR_UNSUPPORTED, "fused all-gather is implemented for k <= 8");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   const void* d_m = nullptr;
   const std::string key = make_key("finv", omega, 32, zs, (size_t)k * 4, n, k);
   int rc = interp_matrix(ctx, key, k, &d_m,
@@ -1059,6 +1073,7 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   if (!omega || d < 0 || k_out < 0 || k_out > n)
     return fail(ctx, HBG_ERR_INVALID, "bad size or null omega");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   if (n < 1 || (n & (n - 1)) != 0) return fail(ctx, HBG_ERR_INVALID, "fft size must be a power of two");
   int rc;
   if (batch == 0 || k_out == 0) {
@@ -1113,6 +1128,7 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
   if (!omega || k < 0 || (k && !zs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
   if (k > 4096) return fail(ctx, HBG_ERR_UNSUPPORTED, "interpolation from more than 4096 points");
   CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
   const void* d_m = nullptr;
   const std::string key = make_key("finv", omega, 32, zs, (size_t)k * 4, n, k);
   int rc = interp_matrix(ctx, key, k, &d_m,

@@ -86,16 +86,34 @@ class Decoder(ABC):
         """z: k party indices; uint64[batch, k, 4] -> uint64[batch, k, 4] coefficients"""
 
 
+class RowFailure:
+    """Outcome of one row of ``robust_decode_batch`` for which the reference's
+    one-row ``robust_decode`` raises (Welch-Berlekamp "No solution" / zero
+    divisor, which reed_solomon.py:205-212 does not swallow).  The batched call
+    must not raise for the whole batch: the reference would only ever reach this
+    row after accepting every row before it (reed_solomon.py:334-365), so the
+    exception travels with the row and is raised by whoever consumes it."""
+
+    __slots__ = ("exc",)
+
+    def __init__(self, exc):
+        self.exc = exc
+
+
 class RobustDecoder(ABC):
     """reed_solomon.py:77-85"""
 
     def robust_decode(self, z, encoded):
-        return self.robust_decode_batch(z, [encoded])[0]
+        out = self.robust_decode_batch(z, [encoded])[0]
+        if isinstance(out, RowFailure):
+            raise out.exc
+        return out
 
     @abstractmethod
     def robust_decode_batch(self, z, rows):
-        """rows: received words on the parties ``z`` -> list of
-        ``(coefficients, sorted error party indices)`` or ``(None, None)``"""
+        """rows: received words on the parties ``z`` -> one entry per row:
+        ``(coefficients, sorted error party indices)``, ``(None, None)``, or a
+        ``RowFailure`` carrying the exception the one-row call raises"""
 
 
 def _points(point, idx):
@@ -229,8 +247,8 @@ class WelchBerlekampRobustDecoder(RobustDecoder):
         zs = [z[i] for i in order]
         rows_sorted = [[row[i] % p for i in order] for row in rows]
         decoded = robust.wb_decode_rows(_points(self.point, zs), rows_sorted, n, n - len(zs), k, p)
-        good = [i for i, c in enumerate(decoded) if c is not None]
-        out = [(None, None)] * len(rows)
+        good = [i for i, c in enumerate(decoded) if isinstance(c, list)]
+        out = [RowFailure(c) if isinstance(c, BaseException) else (None, None) for c in decoded]
         if good:
             width = max(1, max(len(decoded[i]) for i in good))
             ev = unpack_rows(ntl.vandermonde_batch_evaluate_limbs(
@@ -285,8 +303,12 @@ class IncrementalDecoder:
         (``bytes`` of batch*32 little-endian bytes / ``uint64[batch, 4]``, the
         limb wire format of ``batch_reconstruct(..., wire="limbs")``)"""
         if isinstance(data, (bytes, bytearray, memoryview)):
+            if len(data) != self.batch_size * 32:  # a faulty sender must not surface as ValueError
+                raise DecodeValidationError("Incorrect length of data")
             col = np.frombuffer(data, dtype=np.uint64).reshape(-1, 4)
         elif isinstance(data, np.ndarray):
+            if data.size != self.batch_size * 4:
+                raise DecodeValidationError("Incorrect length of data")
             col = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
         else:
             self._check_input(data)
@@ -324,7 +346,10 @@ class IncrementalDecoder:
             rows = unpack_rows(np.stack([c[start:] for c in self._cols], axis=1))
             decoded = self.robust_decoder.robust_decode_batch(list(self._z), rows)
             evicted = False
-            for coeffs, errors in decoded:
+            for outcome in decoded:
+                if isinstance(outcome, RowFailure):
+                    raise outcome.exc  # only now: the rows before it were all accepted
+                coeffs, errors = outcome
                 if coeffs is None or len(self._z) - len(errors) < self._need():
                     return  # wait for more columns
                 self._done_rows.append(coeffs)

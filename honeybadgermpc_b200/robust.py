@@ -90,10 +90,16 @@ def wb_decode_batch_limbs(xs, ys, k, e_max, p):
 
 def wb_decode_rows(xs_ints, rows, n_total, n_erased, k, p):
     """Decode received words (lists of ints on the points ``xs_ints``) the way
-    ``make_wb_encoder_decoder(...).decode`` does (reed_solomon_wb.py:129-151):
-    returns one stripped coefficient list per row, ``None`` for rows where the
-    reference raises ``ValueError("found no divisors!")``; raises like the
-    reference for the other failure modes."""
+    ``make_wb_encoder_decoder(...).decode`` does (reed_solomon_wb.py:129-151).
+    One entry per row: the stripped coefficient list; ``None`` where the
+    reference raises ``ValueError("found no divisors!")`` (swallowed by its
+    caller, reed_solomon.py:205-212); or the EXCEPTION INSTANCE the reference
+    would raise for that row (``"No solution"``, reed_solomon_wb.py:244; the
+    inverse of zero when E(x) vanishes, polynomial.py:219-229 / field.py:133).
+    It is returned, not raised: the reference decodes one row per call, so the
+    caller must raise it only when it gets to that row (reed_solomon.py:334-348).
+    The pre-condition on the number of erasures (reed_solomon_wb.py:132) does not
+    depend on the row and is asserted here."""
     t = k - 1
     assert 2 * t + 1 + n_erased <= n_total
     e_max = (n_total - n_erased - t) // 2
@@ -116,7 +122,7 @@ def wb_decode_rows(xs_ints, rows, n_total, n_erased, k, p):
         elif s == WB_NO_DIVISORS:
             res.append(None)
         elif s == WB_NO_SOLUTION:
-            raise Exception("No solution")  # noqa: TRY002 - what some_solution raises (:244)
+            res.append(Exception("No solution"))
         else:
-            raise ZeroDivisionError("E(x) is the zero polynomial")
+            res.append(ZeroDivisionError("Cannot invert zero"))
     return res

@@ -1,6 +1,7 @@
-"""List reshapes and message plumbing used by ``batch_reconstruct``
-(reference: honeybadgermpc/utils/misc.py:21-106).  Behaviour is the same; the
-``@TypeCheck`` decorators of the reference are not reproduced."""
+"""Message plumbing used by ``batch_reconstruct`` (reference:
+honeybadgermpc/utils/misc.py:76-106).  The reference's list reshapes
+(``chunk_data / transpose_lists / flatten_lists``, utils/misc.py:33-73) have no
+counterpart here: ``batch_reconstruct`` does them as numpy reshapes of limb arrays."""
 
 import asyncio
 import contextlib
@@ -25,35 +26,6 @@ def gc_paused():
     finally:
         if was_enabled:
             gc.enable()
-
-
-def wrap_send(tag, send):
-    """send(dest, msg) -> send(dest, (tag, msg))   (utils/misc.py:21-30)"""
-
-    def tagged(dest, message):
-        send(dest, (tag, message))
-
-    return tagged
-
-
-def chunk_data(data, chunk_size, default=0):
-    """[1,2,3,4,5], 2 -> [[1,2],[3,4],[5,0]]; the empty list gives one flat chunk
-    of defaults, exactly like the reference (utils/misc.py:33-52)."""
-    if not data:
-        return [default] * chunk_size
-    chunks = [list(data[i: i + chunk_size]) for i in range(0, len(data), chunk_size)]
-    chunks[-1].extend([default] * (chunk_size - len(chunks[-1])))
-    return chunks
-
-
-def flatten_lists(lists):
-    return [v for inner in lists for v in inner]
-
-
-def transpose_lists(lists):
-    """[[1,2,3],[4,5,6]] -> [[1,4],[2,5],[3,6]]   (utils/misc.py:67-73)"""
-    width = len(lists[0])
-    return [[row[i] for row in lists] for i in range(width)]
 
 
 def subscribe_recv(recv):

@@ -604,6 +604,10 @@ def wb_solve_system(points, k, p, max_e):
         sol = _some_solution(system, p)
         e_poly = _strip(sol[: e + 1])
         q_poly = _strip(sol[e + 1 :])
+        if not e_poly:
+            # Polynomial.__divmod__ (polynomial.py:219-229) divides by the leading
+            # coefficient of the all-zero E: GFElement inverse of 0 (field.py:133)
+            raise ZeroDivisionError("Cannot invert zero")
         _, rem = poly_divrem(q_poly, e_poly, p)
         if not rem:
             return q_poly, e_poly
@@ -660,3 +664,114 @@ def gao_robust_decode(z, encoded, n, k, p, point):
     if len(err) > 1:
         errors = [i for i in range(n) if poly_eval(err, point(i), p) == 0]
     return decoded, errors
+
+
+# --------------------------------------------------------------------------
+# reed_solomon.py: IncrementalDecoder (the decode inner loop of batch_reconstruct)
+# --------------------------------------------------------------------------
+
+
+class DecodeValidationError(Exception):
+    """reed_solomon.py:228-229"""
+
+
+class IncrementalDecoder:
+    """reed_solomon.py:232-403 restated on plain ints, ONE ROW AT A TIME on the
+    Byzantine path exactly like ``_robust_update`` (:334-365): the first row
+    that must wait stops the loop, so later rows are never decoded in that
+    round, and an exception of the robust decoder surfaces only when the loop
+    reaches the row that causes it.  ``algorithm`` is "gao" or
+    "welch-berlekamp"; the non-robust decoder / encoder are interpolation and
+    evaluation on ``point`` (every reference codec computes the same map)."""
+
+    def __init__(self, point, degree, batch_size, max_errors, algorithm="gao",
+                 confirmed_errors=None, validator=None):
+        self.point, self.p, self.n = point, point.modulus, point.n
+        self.degree, self.batch_size, self.max_errors = degree, batch_size, max_errors
+        self.algorithm, self.validator = algorithm, validator
+        self._confirmed_errors = confirmed_errors if confirmed_errors is not None else set()
+        self._available_points = set()
+        self._z = []
+        self._available_data = [[] for _ in range(batch_size)]
+        self._guess_decoded = self._guess_encoded = None
+        self._optimistic = True
+        self._num_decoded = 0
+        self._partial_result = []
+        self._result = None
+
+    def _robust_decode(self, z, row):
+        fn = gao_robust_decode if self.algorithm == "gao" else wb_robust_decode
+        return fn(z, row, self.n, self.degree + 1, self.p, self.point)
+
+    def _min_points_required(self):  # :302-303
+        return self.degree + 1 + self.max_errors - len(self._confirmed_errors)
+
+    def _optimistic_update(self, idx, data):  # :305-332
+        success = True
+        if len(self._available_points) == self.degree + 1:
+            xs = [self.point(i) for i in self._z]
+            self._guess_decoded = vandermonde_batch_interpolate(xs, self._available_data, self.p) \
+                if self.batch_size else []
+            allx = [self.point(i) for i in range(self.n)]
+            self._guess_encoded = vandermonde_batch_evaluate(allx, self._guess_decoded, self.p) \
+                if self.batch_size else []
+        else:
+            for i in range(self.batch_size):
+                if data[i] % self.p != self._guess_encoded[i][idx]:
+                    success = False
+                    break
+            if not success:
+                self._guess_decoded = self._guess_encoded = None
+                self._optimistic = False
+        if success and len(self._available_points) >= self._min_points_required():
+            self._result = self._guess_decoded
+        return success
+
+    def _robust_update(self):  # :334-365
+        while self._num_decoded < self.batch_size:
+            decoded, errors = self._robust_decode(self._z, self._available_data[0])
+            if decoded is None:
+                break
+            if len(self._available_points) - len(errors) < self._min_points_required():
+                break
+            self._num_decoded += 1
+            self._available_data = self._available_data[1:]
+            self._partial_result.append(decoded)
+            self._confirmed_errors |= set(errors)
+            self._available_points -= set(errors)
+            for e in errors:
+                at = self._z.index(e)
+                del self._z[at]
+                for row in self._available_data:
+                    del row[at]
+        if self._num_decoded == self.batch_size:
+            self._result = self._partial_result
+
+    def add(self, idx, data):  # :368-395
+        if self.done():
+            return
+        if idx in self._available_points or idx in self._confirmed_errors:
+            return
+        if len(data) != self.batch_size:
+            raise DecodeValidationError("Incorrect length of data")
+        if self.validator is not None:
+            for d in data:
+                self.validator(d)
+        self._available_points.add(idx)
+        self._z.append(idx)
+        for i in range(self._num_decoded, self.batch_size):
+            self._available_data[i - self._num_decoded].append(data[i])
+        if len(self._available_points) <= self.degree:
+            return
+        if self._optimistic and self._optimistic_update(idx, data):
+            return
+        if len(self._available_points) >= self._min_points_required():
+            self._robust_update()
+
+    def done(self):
+        return self._result is not None
+
+    def get_results(self):
+        if self._result is not None:
+            return self._result, self._confirmed_errors
+        return None, None

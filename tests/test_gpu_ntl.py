@@ -197,8 +197,9 @@ def test_round_trip_full_size(ntl):
 
 
 def test_empty_and_ragged(ntl):
-    assert ntl.vandermonde_batch_evaluate([1, 2, 3], [[], [1]], P) == [[0, 0, 0], [1, 1, 1]] \
-        or True  # the reference would build a 3x1 matrix; see below
+    # ragged rows are zero-padded to the longest (pyx:217,232-233): d = 1 here
+    assert ntl.vandermonde_batch_evaluate([1, 2, 3], [[], [1]], P) == [[0, 0, 0], [1, 1, 1]]
+    assert orc.vandermonde_batch_evaluate([1, 2, 3], [[], [1]], P) == [[0, 0, 0], [1, 1, 1]]
     assert ntl.vandermonde_batch_evaluate([1, 2, 3], [[7], [1, 1]], P) == [[7, 7, 7], [2, 3, 4]]
     assert ntl.evaluate([], 5, P) == 0
     assert ntl.lagrange_interpolate([], [], P) == []

@@ -146,8 +146,8 @@ def test_incremental_decoder(rs, omega, algo):
         res, errs = inc.get_results()
         assert res == polys and errs == {1, 5}
     else:
-        # Welch-Berlekamp raises "No solution" when a word is beyond capacity (the
-        # reference does not catch it, reed_solomon.py:205-212), so stay within it
+        # one Byzantine party (beyond-capacity words, where the reference's solver raises
+        # "No solution" uncaught, are covered by test_incremental_decoder_differential)
         bad = {4: [0] * batch}
         pt, inc = _inc(rs, n, t, omega, batch, algo)
         for i in [0, 1, 2, 3, 4]:
@@ -167,6 +167,43 @@ def test_incremental_decoder(rs, omega, algo):
     assert inc.done()
     res, errs = inc.get_results()
     assert res == polys and errs == {2}
+
+
+def test_incremental_decoder_differential(rs):
+    """>= 1 000 random Byzantine schedules (tests/differential.py) on the CUDA kernels:
+    the trace of our batched-round decoder must equal the trace of the oracle's
+    row-at-a-time restatement of reed_solomon.py:334-365 AND the digest the reference's own
+    class produced for the same schedule (tests/golden/incremental_traces_v1.json).
+    Schedule 0 is the round-1 Welch-Berlekamp counter-example."""
+    import json
+    import logging
+    import os
+    import sys
+
+    import differential as d
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_incremental_golden as mig
+
+    with open(os.path.join(here, "golden", "incremental_traces_v1.json")) as fh:
+        gold = json.load(fh)
+    logging.disable(logging.CRITICAL)
+    try:
+        ends = {}
+        for seed, (dig, length, end) in enumerate(gold["traces"]):
+            s = d.verdict_fixture() if seed == 0 else d.make_schedule(seed)
+            ours = d.run_trace(d.ours_decoder(s), s)
+            if seed == 0:
+                assert d.to_json(ours) == gold["verdict_fixture_trace"]
+            if seed % 4 == 0:  # the pure-Python oracle is the slow side
+                assert ours == d.run_trace(d.oracle_decoder(s), s), f"schedule {seed} vs oracle"
+            assert (mig.digest(ours), len(ours)) == (dig, length), \
+                f"schedule {seed}: {s['algo']} n={s['n']} omega={s['omega']} {s['field']}"
+            ends[end] = ends.get(end, 0) + 1
+        assert ends["Exception"] > 50 and ends["AssertionError"] > 10 and ends["done"] > 500
+    finally:
+        logging.disable(logging.NOTSET)
 
 
 # --- batch_reconstruct (tests/test_batch_reconstruction.py:12-170) -------------
