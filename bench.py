@@ -106,6 +106,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s), "window": window}
 
 
+def host_threads():
+    """every core this process may run on -- torchrun exports OMP_NUM_THREADS=1, which must
+    not shrink the CPU baseline"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(batch, steps, warmup, threads=0):
     """The CPU restatement of the reference's NTL path (oracle/cpu_ref.cpp) on the
     same workload; returns (shares/s, seconds per step, threads used)."""
@@ -117,6 +126,7 @@ def cpu_reference_run(batch, steps, warmup, threads=0):
 
     graft.build_oracle()
     ref = cpu_ref.CpuRef()
+    threads = threads if threads > 0 else host_threads()
     pt = orc.EvalPoint(P, N_PARTIES, True)
     c = synth(batch, K, 0xB202)
     enc = ref.fft_batch_evaluate_limbs(c, pt.omega, P, pt.order, N_PARTIES, threads=threads)
@@ -130,28 +140,33 @@ def cpu_reference_run(batch, steps, warmup, threads=0):
         r = ref.fft_batch_interpolate_limbs(ZS, y, pt.omega, P, pt.order, threads=threads)
     dt = (time.perf_counter() - t0) / steps
     assert np.array_equal(r, c), "CPU reference round trip failed"
-    used = threads if threads > 0 else ref.max_threads()
-    return batch * K / dt, dt, used
+    return batch * K / dt, dt, threads
 
 
 def run_reference(args):
+    """The reference arm: the CPU implementation of the path (the C++ restatement of
+    rsdecode_impl.h -- NTL itself cannot be installed here) on this box's host cores, same
+    workload, batch and warm-up as the B200 arm; the step count is bounded so the run
+    stays within about a minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8192
-    steps = max(1, min(args.steps, 40))
-    warm = max(1, min(args.warmup, 3))
-    value, dt, cores = cpu_reference_run(sample, steps, warm)
+    batch = args.batch
+    probe_v, probe_dt, cores = cpu_reference_run(batch, 1, 1)
+    steps = max(3, min(args.steps, int(45.0 / probe_dt)))
+    value, dt, cores = cpu_reference_run(batch, steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 mod p",
         "data": "synthetic",
         "config": {"workload": "n=16 t=5 NTT encode+interpolate (BASELINE configs[1])",
-                   "batch_polys_per_step": sample, "shares_per_poly": K, "field": "BLS12-381 r"},
+                   "batch_polys_per_step": batch, "shares_per_poly": K, "field": "BLS12-381 r", "z": ZS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} polynomials x {steps} steps; C++ restatement of "
-                                   "rsdecode_impl.h (NTL itself is not installable here)"},
+                         "sample": f"{batch} polynomials x {steps} steps on {cores} threads (explicit, "
+                                   "OMP_NUM_THREADS ignored); C++ restatement of rsdecode_impl.h "
+                                   "(NTL itself is not installable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,7 +182,7 @@ def run_b200(args):
     from honeybadgermpc_b200.field import GF
     from honeybadgermpc_b200.ntl import pack_vec
     from honeybadgermpc_b200.polynomial import EvalPoint
-    from honeybadgermpc_b200.sharding import all_gather_rows
+    from honeybadgermpc_b200.sharding import ShardedReconstructor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,16 +197,20 @@ def run_b200(args):
     batch, sets = args.batch, args.sets
     pt = EvalPoint(GF(P), N_PARTIES, True)
     omega = pack_vec([pt.omega.value], P)[0]
-    ctx = _native.Context(P, device=local)
-    stream = torch.cuda.Stream(device=dev)
-    ctx.set_stream(stream.cuda_stream)
+    # the sharded reconstructor owns the interpolation context / stream and the gather slots
+    depth = sets if world == 1 else min(3, sets)
+    rec = ShardedReconstructor(P, omega, pt.order, ZS, batch, device=local, depth=depth,
+                               gather=args.gather, copy_ctas=args.gather_ctas)
+    ctx, stream = rec.ctx, rec.stream
+    if args.matvec_path != "auto":
+        ctx.set_matvec_path(args.matvec_path)
 
     def dev_u64(a):
         return torch.from_numpy(a.view(np.int64)).to(dev)
 
     # ---- synthetic inputs, resident in HBM; `sets` rotating buffer sets so every
     # step reads cold data (sets * 71 MB >> 126 MB of L2)
-    c, e, y, r = [], [], [], []
+    c, e, y = [], [], []
     zs_t = torch.tensor(ZS, device=dev)
     with torch.cuda.stream(stream):
         for s in range(sets):
@@ -204,213 +223,153 @@ def run_b200(args):
             c.append(cs)
             e.append(es)
             y.append(ys)
-            r.append(torch.zeros((batch, K, 4), dtype=torch.int64, device=dev))
-        depth = min(3, sets)
-        gathered, handles, gather_mode = [], [], "none"
-        if world > 1 and args.gather != "nccl":
-            # symmetric memory: every rank's gather buffer mapped into every process, plus an
-            # NVSwitch multicast address when the fabric offers one -> the interpolation kernel
-            # stores its block straight into all ranks' buffers (fused compute + all-gather)
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-
-                for _ in range(depth):
-                    buf = symm_mem.empty((world * batch, K, 4), dtype=torch.int64, device=dev)
-                    handles.append(symm_mem.rendezvous(buf, dist.group.WORLD))
-                    gathered.append(buf)
-                mc = int(getattr(handles[0], "multicast_ptr", 0) or 0)
-                if args.gather == "copy":
-                    gather_mode = "multimem-copy" if mc else "p2p-copy"
-                elif args.gather == "auto":
-                    gather_mode = "fused-multimem" if mc else "fused-p2p"
-                else:
-                    gather_mode = "fused-p2p"
-            except Exception as exc:  # noqa: BLE001
-                if rank == 0:
-                    print(f"[bench] symmetric memory unavailable ({exc!r}); using NCCL all-gather",
-                          file=sys.stderr)
-                gathered, handles = [], []
-        if world > 1 and not handles:
-            gather_mode = "nccl-overlapped"
-            gathered = [torch.empty((world * batch, K, 4), dtype=torch.int64, device=dev)
-                        for _ in range(depth)]
-        pending = [None] * len(gathered)
-        slot_done = [None] * len(gathered)
-        side = torch.cuda.Stream(device=dev)
-        # per-slot constants of the gather, marshalled once (the step loop is host-time critical)
-        slot_peers = [_native.Context.peer_array(list(h.buffer_ptrs)) for h in handles]
-        slot_mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles]
-        written_ev = [torch.cuda.Event() for _ in handles]
-        done_ev = [torch.cuda.Event() for _ in handles]
-    zs32 = np.ascontiguousarray(ZS, dtype=np.int32)
     stream.synchronize()
-
     names = {"encode": ctx.last_kernel()}  # the set-up loop above ended with an encode
     c_ptr = [t.data_ptr() for t in c]
     e_ptr = [t.data_ptr() for t in e]
     y_ptr = [t.data_ptr() for t in y]
-    r_ptr = [t.data_ptr() for t in r]
 
-    # For N > 1 the all-gather of the decoded block is fused into the interpolation kernel (or runs
-    # on a side stream, see below) and the independent encode of the step runs on a second stream:
-    # the fused kernel leaves SM time free while it waits on NVLink.  Measured at 8 ranks with the
-    # current kernels: 2.19e10 shares/s with the encode overlapped, 2.02e10 in order (with the
-    # first kernels of this round it was the other way round: 1.91e10 against 2.18e10).
-    # N = 1: the encode and the interpolation of a step are independent launches, so they go
-    # to two streams: each kernel fills the GPU in a single wave (1024 CTAs for 1036 slots)
-    # and spends ~8 us of its ~30 us ramping up and draining; on two streams the next
-    # kernel's CTAs take over SM by SM as the previous kernel's CTAs retire.  The per-kernel
-    # durations of the roofline come from a second, serial pass over the same steps.
-    overlap_encode = (world > 1 and gather_mode.startswith("fused")) or (world == 1 and not args.serial)
+    # The encode and the interpolation of a step are independent launches: they go to two
+    # streams, so one kernel's CTAs take over SM by SM as the other's retire and neither's
+    # fill / drain phase is exposed.  The per-kernel durations of the roofline come from a
+    # second, serial pass over the same steps.
+    overlap_encode = not args.serial
     if args.overlap_encode != "auto":
         overlap_encode = args.overlap_encode == "on"
     enc_stream = torch.cuda.Stream(device=dev) if overlap_encode else stream
-
-    # one context per stream (no hbg_ctx_set_stream inside the step loop: the loop is host-time
-    # critical -- a step is ~40 us of GPU work)
     ctx_enc = _native.Context(P, device=local) if overlap_encode else ctx
     ctx_enc.set_stream(enc_stream.cuda_stream)
+    if args.matvec_path != "auto":
+        ctx_enc.set_matvec_path(args.matvec_path)
 
-    def step(s, evs=None):
+    def encode(s):
+        ctx_enc.fft_batch_evaluate(omega, pt.order, c_ptr[s], batch, K, N_PARTIES, e_ptr[s], _native.MEM_DEVICE)
+
+    def step(i, evs=None):
+        s = i % sets
         if evs is not None:
             evs[0].record(enc_stream)
-        ctx_enc.fft_batch_evaluate(omega, pt.order, c_ptr[s], batch, K, N_PARTIES, e_ptr[s], _native.MEM_DEVICE)
+        encode(s)
         if evs is not None:
             evs[1].record(enc_stream)
-        if evs is not None and overlap_encode:
-            evs[3].record(stream)
-        fused = handles and gather_mode.startswith("fused")
-        if handles:
-            slot = s % len(gathered)
-            h = handles[slot]
-            if slot_done[slot] is not None:
-                stream.wait_event(slot_done[slot])  # the previous gather into this slot is complete everywhere
-        if fused:
-            use_mc = slot_mc[slot] if gather_mode == "fused-multimem" else 0
-            ctx.fft_batch_interpolate_allgather(omega, pt.order, zs32, y_ptr[s], batch,
-                                                slot_peers[slot], use_mc, rank)
-        else:
-            ctx.fft_batch_interpolate(omega, pt.order, zs32, y_ptr[s], batch, r_ptr[s],
-                                      _native.MEM_DEVICE)
+            if overlap_encode:
+                evs[3].record(stream)
+        rec.open(y_ptr[s], slot=i % depth)
         if evs is not None:
             evs[2].record(stream)
-        if handles:
-            # completion of the gather (= every rank's block has landed in every buffer) is a
-            # device-side barrier over the symmetric-memory signal pads; it runs on a side
-            # stream so this rank's next encode does not wait for the slowest rank
-            slot = s % len(gathered)
-            written = written_ev[slot]
-            written.record(stream)
-            side.wait_event(written)
-            if not fused:
-                # copy kernel: a few CTAs push this rank's block into every rank's buffer
-                # (multimem.st -> replicated by the NVSwitch) while `stream` moves on
-                ctx.set_stream(side.cuda_stream)
-                ctx.allgather_block(r_ptr[s], batch * K * E, slot_peers[slot],
-                                    slot_mc[slot] if gather_mode == "multimem-copy" else 0,
-                                    rank * batch * K * E, args.gather_ctas)
-                ctx.set_stream(stream.cuda_stream)
-            handles[slot].barrier()  # on torch's current stream = `side` (set around the step loops)
-            slot_done[slot] = done_ev[slot]
-            slot_done[slot].record(side)
-        elif world > 1:
-            # the one collective of the path: reassemble the decoded blocks on every rank.
-            # It runs on NCCL's stream and overlaps the next step's kernels; the buffer
-            # pair (r[s], gathered[slot]) is only reused after its gather has completed.
-            slot = s % len(gathered)
-            if pending[slot] is not None:
-                pending[slot].wait()
-            _, pending[slot] = all_gather_rows(r[s], world * batch, out=gathered[slot], async_op=True)
 
     def barrier():
-        for i, w in enumerate(pending):
-            if w is not None:
-                w.wait()
-                pending[i] = None
+        rec.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # torch's *current* stream only matters for the symmetric-memory barrier of the fused
-    # gather (our kernels and events name their streams explicitly): make it `side` once
-    # instead of entering a stream context on every step
-    with torch.cuda.stream(side if handles else stream):
-        sampler = ClockSampler(local)
-        sampler.start()
-        for i in range(args.warmup):
-            step(i % sets)
-            if i == 0:
-                names["interpolate"] = ctx.last_kernel()
-        barrier()
-        # per-kernel events: every step when the kernels run in order on one stream; with
-        # overlapped streams only every `--event-every`-th step (they cost host time, and for
-        # N = 1 the roofline durations come from the serial pass anyway)
-        ev_every = 1 if not overlap_encode else max(1, args.event_every)
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] if i % ev_every == 0 else None
-               for i in range(args.steps)]
-        t_start = torch.cuda.Event(enable_timing=True)
-        t_end = torch.cuda.Event(enable_timing=True)
-        launches0 = ctx.launch_count() + (ctx_enc.launch_count() if ctx_enc is not ctx else 0)
-        barrier()
-        host_t0 = time.perf_counter()
-        t_start.record(stream)
-        for i in range(args.steps):
-            step((args.warmup + i) % sets, evs[i])
-        stream.wait_stream(enc_stream)
-        t_end.record(stream)
-        host_enqueued = time.perf_counter()
-        barrier()
-        host_t1 = time.perf_counter()
-        launches = ctx.launch_count() + (ctx_enc.launch_count() if ctx_enc is not ctx else 0) - launches0
-        serial_evs = None
-        if world == 1 and overlap_encode:
-            # serial pass (not part of `value`): the same steps with both kernels on one stream,
-            # so each kernel's CUDA-event duration is its own
-            enc_stream_saved, enc_stream = enc_stream, stream
-            ctx_enc.set_stream(stream.cuda_stream)
-            serial_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                          for _ in range(min(args.steps, 200))]
-            for i, ev in enumerate(serial_evs):
-                step((args.warmup + i) % sets, ev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(max(args.warmup, sets)):
+        step(i)
+        if i == 0:
+            names["interpolate"] = ctx.last_kernel()
+    barrier()
+
+    # ---- the timed region: `unit` = lcm(sets, depth) consecutive steps captured into ONE CUDA
+    # graph (the Python step loop costs ~20 us per step, more than the GPU work of a step),
+    # replayed until at least --steps steps AND --min-ms of device time have run
+    unit = int(sets * depth // np.gcd(sets, depth))
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = rec.capture(
+                [y_ptr[i % sets] for i in range(unit)],
+                begin=(lambda: enc_stream.wait_stream(stream)) if overlap_encode else None,
+                extra=lambda i: encode(i % sets),
+                finish=(lambda: stream.wait_stream(enc_stream)) if overlap_encode else None)
+        except Exception as exc:  # noqa: BLE001 - e.g. a collective that cannot be captured
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({exc!r}); eager step loop", file=sys.stderr)
+            graph = None
             barrier()
-            enc_stream = enc_stream_saved
-            ctx_enc.set_stream(enc_stream.cuda_stream)
-        sampler.stop_flag.set()
-        sampler.join()
+    launches_per_step = 2 + (1 if rec.mode.endswith("copy") else 0)
+
+    def run_steps(n_steps):
+        """enqueue n_steps (a multiple of `unit` when the graph is used)"""
+        if graph is not None:
+            with torch.cuda.stream(stream):
+                for _ in range(n_steps // unit):
+                    graph.replay()
+        else:
+            for i in range(n_steps):
+                step(i)
+            stream.wait_stream(enc_stream)
+
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    # calibration: how many steps make --min-ms
+    barrier()
+    t_start.record(stream)
+    run_steps(unit * 4)
+    t_end.record(stream)
+    barrier()
+    est_ms = t_start.elapsed_time(t_end) / (unit * 4)
+    if world > 1:
+        tt = torch.tensor([est_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        est_ms = float(tt.item())
+    steps = max(args.steps, int(np.ceil(args.min_ms / est_ms)))
+    steps = int(np.ceil(steps / unit)) * unit
+    barrier()
+    host_t0 = time.perf_counter()
+    t_start.record(stream)
+    run_steps(steps)
+    t_end.record(stream)
+    host_enqueued = time.perf_counter()
+    barrier()
+    host_t1 = time.perf_counter()
     total_ms = t_start.elapsed_time(t_end)
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-    timed = [ev for ev in evs if ev is not None]
-    enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in timed) / len(timed)
-    dec_ms = sum(ev[3 if overlap_encode else 1].elapsed_time(ev[2]) for ev in timed) / len(timed)
-    overlapped_ms = None
-    if serial_evs is not None:
-        overlapped_ms = {"encode": enc_ms, "interpolate": dec_ms}
-        enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in serial_evs) / len(serial_evs)
-        dec_ms = sum(ev[1].elapsed_time(ev[2]) for ev in serial_evs) / len(serial_evs)
+    sampler.stop_flag.set()
+    sampler.join()
 
-    # parity inside the bench: every decoded block equals its coefficients
-    used = min(sets, args.warmup + args.steps)
-    if handles:
-        last = (args.warmup + args.steps - 1) % sets
-        g = gathered[last % len(gathered)]
-        assert torch.equal(g[rank * batch:(rank + 1) * batch], c[last]), "gather: own block mismatch"
-        sums = g.view(world, -1).sum(dim=1)
-        lo, hi = sums.clone(), sums.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert torch.equal(lo, hi), "fused gather: ranks disagree on the gathered blocks"
-    else:
-        for s in range(used):
-            assert torch.equal(r[s], c[s]), f"round trip mismatch in buffer set {s}"
+    # ---- parity inside the bench, on what the timed steps left behind: every buffer set's
+    # encode output restricted to z equals the interpolation input, the gathered blocks equal
+    # the coefficients on every rank
+    for s in range(sets):
+        assert torch.equal(e[s].index_select(1, zs_t), y[s]), f"encode output of buffer set {s} is wrong"
+    last = steps - 1
+    for back in range(min(depth, steps)):
+        i = last - back
+        g = rec.gathered[i % depth]
+        assert torch.equal(g[rank * batch:(rank + 1) * batch], c[i % sets]), \
+            f"step {i}: decoded block != coefficients"
         if world > 1:
-            last = (args.warmup + args.steps - 1) % sets
-            assert torch.equal(gathered[last % len(gathered)][rank * batch:(rank + 1) * batch], r[last])
+            sums = g.view(world, -1).sum(dim=1)
+            lo, hi = sums.clone(), sums.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi), "all-gather: ranks disagree on the gathered blocks"
 
-    ms_per_step = total_ms / args.steps
+    # ---- serial pass (not part of `value`): the same steps, eager, both kernels on one stream,
+    # so each kernel's CUDA-event duration is its own
+    enc_saved = enc_stream
+    enc_stream = stream
+    ctx_enc.set_stream(stream.cuda_stream)
+    n_serial = min(max(args.steps, 20), 200)
+    serial_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_serial)]
+    overlap_saved, overlap_encode = overlap_encode, False
+    for i, ev in enumerate(serial_evs):
+        step(i, ev)
+    barrier()
+    overlap_encode = overlap_saved
+    enc_stream = enc_saved
+    ctx_enc.set_stream(enc_stream.cuda_stream)
+    enc_ms = sum(ev[0].elapsed_time(ev[1]) for ev in serial_evs) / n_serial
+    dec_ms = sum(ev[1].elapsed_time(ev[2]) for ev in serial_evs) / n_serial
+
+    ms_per_step = total_ms / steps
     value = world * batch * K / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (algorithmic bytes, DESIGN.md section 4)
@@ -429,32 +388,41 @@ def run_b200(args):
     else:
         dom, dom_ms, dom_bytes = "interpolate", dec_ms, dec_bytes
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(names[dom])
+            tj = json.load(fh)
+        traffic = tj.get(f"{dom}:{names[dom]}")
+        traffic_src = tj.get("source")
     except (OSError, ValueError):
         pass
-    # the binding resource is the 64-bit integer multiply-add pipe: algorithmic
-    # IMAD.WIDE per polynomial against the measured pipe rate
-    # (tools/microbench3.cu on this pool: carry chains of IMAD.WIDE at 31 per clock per SM =
-    # 9.0e12 /s at 1965 MHz; one warp-wide IMAD.WIDE holds the fmaheavy pipe for 4 cycles)
-    imad = {"encode": 15 * 103, "interpolate": K * K * 64 + K * 48}
-    imad_peak = 9.0e12
-    imad_rate = imad[dom] * batch / (dom_ms * 1e-3)
+    # u8 multiply-accumulates of the tensor-core kernel (K = 32 d bytes per row, 32 columns per
+    # output) against the nominal dense 8-bit rate
+    macs = {"encode": N_PARTIES * 32 * K * 32, "interpolate": K * 32 * K * 32}
+    nb_link = (world - 1) * batch * K * E  # bytes every rank must RECEIVE per step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "kernel": f"{dom}: {names[dom]}",
-                "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src or "none committed for this kernel",
+                "kernel": f"{dom}: {names[dom]}", "peak_source": peak_src,
                 "kernel_ms": {"encode": enc_ms, "interpolate": dec_ms}, "kernels": names,
-                "kernel_ms_source": ("serial pass after the timed region (the timed steps overlap the two "
-                                     "kernels on two streams)" if serial_evs is not None else "timed region"),
-                "kernel_ms_overlapped": overlapped_ms,
+                "kernel_ms_source": "serial eager pass after the timed region (the timed steps overlap "
+                                    "the two kernels on two streams inside a CUDA graph)",
                 "step_GBps": (enc_bytes + dec_bytes) / (ms_per_step * 1e-3) / 1e9,
-                "int_pipe": {"achieved_imad_wide_per_s": imad_rate, "peak_imad_wide_per_s": imad_peak,
-                             "frac": imad_rate / imad_peak,
-                             "imad_wide_per_polynomial": imad[dom]},
-                "note": "256-bit modular arithmetic: the kernel is bound by the IMAD.WIDE pipe, not by "
-                        "HBM (DESIGN.md section 4); both fractions are reported"}
+                "step_frac": (enc_bytes + dec_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
+                "tensor": {"u8_mac_per_s": macs[dom] * batch / (dom_ms * 1e-3),
+                           "nominal_u8_mac_per_s": 2.25e15,
+                           "note": "exact u8 x u8 -> s32 GEMM on tcgen05 (kind::i8); the kernel is bound "
+                                   "by HBM / the TMEM-read epilogue, not by the MMA rate"},
+                "note": "256-bit modular arithmetic as an integer GEMM whose constant operand absorbs "
+                        "the reduction (DESIGN.md section 4)"}
+    if world > 1:
+        link = 770.0  # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
+        roofline["nvlink"] = {"ingress_bytes_per_step": nb_link, "link_GBps": link,
+                              "floor_ms_per_step": nb_link / link / 1e6,
+                              "achieved_GBps": nb_link / (ms_per_step * 1e-3) / 1e9,
+                              "frac": nb_link / (ms_per_step * 1e-3) / 1e9 / link,
+                              "note": "every rank receives the other ranks' decoded blocks: for N >= 4 the "
+                                      "step is bound by NVLink ingress, not by the kernels"}
 
     # ---- end to end: the C-ABI call a reference-side binding makes, HOST buffers
     # (pinned), H2D + kernel + D2H inside the timed region
@@ -490,6 +458,7 @@ def run_b200(args):
     per_step = sorted(b - a for a, b in zip(marks, marks[1:]))
     ctx.set_host_async(False)
     assert torch.equal(hr, hc), "end-to-end round trip mismatch"
+    assert torch.equal(he[:, ZS, :], hy), "end-to-end encode mismatch"
     if world > 1:
         tt = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -514,9 +483,12 @@ def run_b200(args):
                              "oracle/cpu_ref.cpp (C++ restatement of rsdecode_impl.h, OpenMP over the batch)",
                    "ms_per_step": dt * 1e3}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 Montgomery (256-bit integer mod p)",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "steps_requested": args.steps,
+            "warmup": max(args.warmup, sets), "ms_per_step": ms_per_step, "timed_region_ms": total_ms,
+            "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32 tensor-core GEMM + 256-bit "
+                                                             "integer reduction mod p (exact)",
             "data": "synthetic",
             "config": {"workload": "n=16 t=5 NTT encode+interpolate (BASELINE configs[1])",
                        "batch_polys_per_gpu": batch, "shares_per_poly": K,
@@ -525,16 +497,16 @@ def run_b200(args):
                              "(inputs+outputs larger than the 126 MB L2)",
                        "streams": ("encode and interpolate of a step on two streams" if overlap_encode
                                    else "one stream"),
-                       "parallelism": f"batch shard x{world}" + (
-                           f" + all-gather ({gather_mode})"
-                           + (", encode overlapped on a second stream" if overlap_encode else "")
-                           if world > 1 else ""),
+                       "step_loop": (f"CUDA graph of {unit} steps, replayed" if graph is not None
+                                     else "eager Python loop"),
+                       "parallelism": f"batch shard x{world}" + (f" + all-gather ({rec.mode})" if world > 1 else ""),
                        "polys_per_s": value / K},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "host_enqueue_ms_per_step": (host_enqueued - host_t0) * 1e3 / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * steps,
+            "host_enqueue_ms_per_step": (host_enqueued - host_t0) * 1e3 / steps,
             "clocks": sampler.result(host_t0, host_t1),
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -562,6 +534,11 @@ def main():
                          "p2p = the same with peer stores only; copy = separate side-stream copy kernel; "
                          "nccl = overlapped NCCL all-gather")
     ap.add_argument("--gather-ctas", type=int, default=16)
+    ap.add_argument("--min-ms", type=float, default=60.0,
+                    help="the timed region is extended (more steps) until it lasts at least this long")
+    ap.add_argument("--no-graph", action="store_true", help="eager Python step loop instead of a CUDA graph")
+    ap.add_argument("--matvec-path", default="auto",
+                    help="auto (tensor-core kernel) | no-tc (the IMAD kernels of round 1) | ...")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

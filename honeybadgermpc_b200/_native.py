@@ -91,6 +91,18 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
          ctypes.c_int]),
+    "hbg_ctx_set_cache_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "hbg_columns_to_rows": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "hbg_interpolate_reencode": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]),
+    "hbg_compare_columns": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 
@@ -193,7 +205,8 @@ class Context:
 
     def set_matvec_path(self, path):
         self._check(self.lib.hbg_ctx_set_matvec_path(
-            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3, "small-r29": 4}[path]))
+            self.handle, {"auto": 0, "global": 1, "smem": 2, "small": 3, "small-r29": 4, "tc": 5,
+                          "no-tc": 6}[path]))
 
     # -- batch operations (limb arrays or device pointers) ------------------
     def vandermonde_batch_evaluate(self, xs, polys, batch, d, out, mem=MEM_HOST):
@@ -235,6 +248,26 @@ class Context:
         self._check(self.lib.hbg_allgather_block(
             self.handle, int(block_ptr), nbytes, arr, int(multicast_ptr) if multicast_ptr else None,
             offset_bytes, len(peer_ptrs), max_ctas))
+
+    # -- device-resident IncrementalDecoder -----------------------------------
+    def set_cache_limit(self, nbytes):
+        self._check(self.lib.hbg_ctx_set_cache_limit(self.handle, int(nbytes)))
+
+    def columns_to_rows(self, colbuf_ptr, batch, idx, rows_ptr):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._check(self.lib.hbg_columns_to_rows(self.handle, int(colbuf_ptr), batch, _ptr(idx), len(idx),
+                                                 int(rows_ptr)))
+
+    def interpolate_reencode(self, xs_k, xs_all, ys, batch, out, mem=MEM_HOST):
+        self._check(self.lib.hbg_interpolate_reencode(
+            self.handle, _ptr(xs_k), len(xs_k), _ptr(xs_all), len(xs_all), _ptr(ys), batch, _ptr(out), mem))
+
+    def compare_columns(self, rows_ptr, row_width, col_offset, colbuf_ptr, batch, idx, flags_dev_ptr,
+                        flags_host=None):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._check(self.lib.hbg_compare_columns(
+            self.handle, int(rows_ptr), row_width, col_offset, int(colbuf_ptr), batch, _ptr(idx), len(idx),
+            int(flags_dev_ptr), _ptr(flags_host)))
 
     def gao_decode_batch(self, xs, k, ys, batch, coeffs, locator, loc_stride, loc_len, status,
                          mem=MEM_HOST):

@@ -17,6 +17,7 @@
 #include "host_math.hpp"
 #include "kernels.cuh"
 #include "robust_kernels.cuh"
+#include "tc_kernels.cuh"
 
 using namespace hb;
 
@@ -48,7 +49,10 @@ struct hbg_ctx {
                         // 4 ntt with the register-resident split kernel for n = 16,
                         // 5 ntt, n = 16 with the balanced (hand-over) form of the 4-point-group kernel
   int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel,
-                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic
+                        // 4 small-k kernel with the carry-free radix-2^29 arithmetic,
+                        // 5 tensor-core kernel (tc_kernels.cuh), 6 never the tensor-core kernel
+  unsigned tc_mu = 0;   // floor(2^280 / p) when the tensor-core path serves this modulus, else 0
+  unsigned* tc_error = nullptr;  // device word set by a barrier watchdog of tc_apply_kernel
   int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
   std::string err;
   uint64_t launches = 0;
@@ -68,6 +72,8 @@ struct hbg_ctx {
   std::unordered_map<std::string, DevConst> cache;
   std::unordered_map<std::string, std::vector<uint32_t>> host_cache;  // small tables passed by value
   size_t cache_bytes = 0;
+  size_t cache_limit = (size_t)256 << 20;
+  DevBuf flags;  // hbg_compare_columns: staging for flags_host
 };
 
 namespace {
@@ -128,7 +134,7 @@ int ensure(hbg_ctx* ctx, DevBuf& b, size_t bytes) {
 // get_const: a call may hold several cached pointers at once (Gao: the interpolation matrix
 // and g0), and kernels of earlier calls on this stream may still be reading theirs.
 int cache_trim(hbg_ctx* ctx) {
-  if (ctx->cache_bytes <= ((size_t)256 << 20)) return HBG_OK;
+  if (ctx->cache_bytes <= ctx->cache_limit) return HBG_OK;
   CU(cudaStreamSynchronize(ctx->stream));
   for (auto& kv : ctx->cache) cudaFree(kv.second.p);
   ctx->cache.clear();
@@ -316,6 +322,126 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
   ctx->launches++;
   ctx->last_kernel = "apply_matrix_kernel";
   return HBG_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// tensor-core path (tc_kernels.cuh): out[b] = M in[b] as an exact u8 GEMM
+// ---------------------------------------------------------------------------
+struct TcPlan {
+  unsigned ob, n_blocks, stages, ew;
+  size_t b_bytes, smem;
+};
+
+const size_t kTcMinBatch = 512;  // below this the IMAD kernels' latency wins (auto mode)
+
+// Shape check: the constant operand (32 n_out x 32 d bytes) stays resident in shared
+// memory next to >= 3 stages of 128-row input tiles.
+bool tc_plan(int n_out, int d, TcPlan* pl) {
+  if (n_out < 1 || d < 1 || d > 1024) return false;
+  pl->ob = n_out <= 8 ? (unsigned)n_out : 8u;
+  pl->n_blocks = ((unsigned)n_out + pl->ob - 1) / pl->ob;
+  pl->b_bytes = (size_t)32 * pl->ob * 32 * d * pl->n_blocks;
+  const size_t stage = tc_stage_bytes(32u * d);
+  const size_t b_al = (pl->b_bytes + 1023) & ~(size_t)1023;
+  const size_t room = kMaxSmem - 1024;  // the kernel may skip up to 1008 bytes to align its window
+  if (b_al + 2 * stage > room) return false;  // >= 2 stages: one tile in flight behind the MMA
+  size_t st = (room - b_al) / stage;
+  pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
+  pl->ew = pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
+  pl->smem = tc_smem_bytes(32u * d, pl->n_blocks, pl->ob, pl->stages) + 1024;
+  return true;
+}
+
+bool tc_wanted(const hbg_ctx* ctx, int n_out, int d, size_t batch, TcPlan* pl) {
+  if (!ctx->tc_mu || ctx->matvec_path == 6 || (ctx->matvec_path >= 1 && ctx->matvec_path <= 4)) return false;
+  if (!tc_plan(n_out, d, pl)) return false;
+  return ctx->matvec_path == 5 || batch >= kTcMinBatch;
+}
+
+// The constant operand of the u8 GEMM for a row-major n_out x d matrix in Montgomery form:
+// B[(i,c)][(j,a)] = byte c of (M[i][j] * 2^(8a) mod p), laid out block by block in the UMMA
+// canonical K-major form (16-byte K chunks; chunk (n, kc) of a block at kc * NB*16 + n*16).
+void tc_build_bmat(const HostField& f, const std::vector<Fe>& m_mont, int n_out, int d, const TcPlan& pl,
+                   std::vector<uint32_t>& host) {
+  const unsigned NB = 32 * pl.ob, K = 32u * d;
+  host.assign(pl.b_bytes / 4, 0);
+  uint8_t* b = (uint8_t*)host.data();
+  const Fe c256 = f.from_small(256);
+  for (int i = 0; i < n_out; i++)
+    for (int j = 0; j < d; j++) {
+      Fe cur = m_mont[(size_t)i * d + j];
+      const unsigned nb = i / pl.ob, o = i % pl.ob;
+      for (unsigned a = 0; a < 32; a++) {
+        const Fe s = f.from_mont(cur);
+        const uint8_t* bytes = (const uint8_t*)s.w;
+        const unsigned kb = j * 32 + a;
+        uint8_t* dst = b + (size_t)nb * NB * K + (size_t)(kb / 16) * (NB * 16) + kb % 16;
+        for (unsigned c = 0; c < 32; c++) dst[(size_t)(o * 32 + c) * 16] = bytes[c];
+        cur = f.mul(cur, c256);
+      }
+    }
+}
+
+template <int EW>
+int launch_tc_ew(hbg_ctx* ctx, const CUtensorMap& tm, const TcArgs& a, const TcPlan& pl, unsigned grid) {
+  int rc = allow_big_smem(ctx, tc_apply_kernel<FieldBLS, EW>);
+  if (rc) return rc;
+  tc_apply_kernel<FieldBLS, EW><<<grid, (EW + kTcLoadWarps + 1) * 32, pl.smem, ctx->stream>>>(tm, a);
+  return HBG_OK;
+}
+
+int launch_tc(hbg_ctx* ctx, const void* d_b, const TcPlan& pl, int n_out, int d, const void* d_in,
+              size_t in_pitch, void* d_out, size_t out_pitch, size_t batch,
+              const GatherDst* gather = nullptr, size_t gather_row0 = 0) {
+  if (batch == 0) return HBG_OK;
+  TcArgs a;
+  memset(&a, 0, sizeof a);
+  if (gather) {
+    a.gather_world = (unsigned)gather->world;
+    a.gather_mc = (uint8_t*)gather->mc;
+    for (int r = 0; r < gather->world; r++) a.gather_peers[r] = (uint8_t*)gather->peers[r];
+    a.gather_row0 = gather_row0;
+  }
+  a.in = (const uint8_t*)d_in;
+  a.bmat = (const uint8_t*)d_b;
+  a.out = (uint8_t*)d_out;
+  a.batch = batch;
+  a.K = 32u * d;
+  a.n_out = n_out;
+  a.ob = pl.ob;
+  a.n_blocks = pl.n_blocks;
+  a.in_pitch = (unsigned)in_pitch;
+  a.out_pitch = (unsigned)out_pitch;
+  a.stages = pl.stages;
+  a.mu = ctx->tc_mu;
+  a.error = ctx->tc_error;
+  const size_t tiles = (batch + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < (size_t)ctx->sm_count ? tiles : (size_t)ctx->sm_count);
+  CUtensorMap tm;
+  if (!tc_make_tmap(&tm, d_in, batch, a.K, in_pitch))
+    return fail(ctx, HBG_ERR_CUDA, "cuTensorMapEncodeTiled failed (input must be 16-byte aligned)");
+  int rc = pl.ew == 16 ? launch_tc_ew<16>(ctx, tm, a, pl, grid)
+         : pl.ew == 12 ? launch_tc_ew<12>(ctx, tm, a, pl, grid)
+                       : launch_tc_ew<8>(ctx, tm, a, pl, grid);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "tc_apply_kernel";
+  return HBG_OK;
+}
+
+// Cached tensor-core operand for the matrix `gen` produces (row-major, Montgomery form).
+template <class Gen>
+int tc_const(hbg_ctx* ctx, const std::string& key, int n_out, int d, const TcPlan& pl, const void** d_b,
+             Gen gen) {
+  return get_const(ctx, key + "|tc", d_b, [&](std::vector<uint32_t>& host) {
+    std::vector<Fe> m;
+    int rc = gen(m);
+    if (rc) return rc;
+    tc_build_bmat(*ctx->field, m, n_out, d, pl, host);
+    return HBG_OK;
+  });
 }
 
 int ilog2(int n) {
@@ -862,6 +988,14 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
   }
   ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (ctx->is_bls) {  // the tensor-core path is instantiated for the BLS12-381 scalar field
+    ctx->tc_mu = barrett_mu280(fp);
+    if (cudaMalloc(&ctx->tc_error, sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(ctx->tc_error, 0, sizeof(unsigned)) != cudaSuccess) {
+      ctx->tc_mu = 0;
+      ctx->tc_error = nullptr;
+    }
+  }
   *out = ctx;
   return HBG_OK;
 }
@@ -875,6 +1009,8 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->out.p) cudaFree(ctx->out.p);
   if (ctx->work.p) cudaFree(ctx->work.p);
   if (ctx->work2.p) cudaFree(ctx->work2.p);
+  if (ctx->tc_error) cudaFree(ctx->tc_error);
+  if (ctx->flags.p) cudaFree(ctx->flags.p);
   if (ctx->s_in) {
     cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->s_out);
@@ -928,7 +1064,8 @@ uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx) { return ctx ? ctx->launches :
 const char* hbg_ctx_last_kernel(const hbg_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 4) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 6) return HBG_ERR_INVALID;
+  if (path == 5 && !ctx->tc_mu) return fail(ctx, HBG_ERR_UNSUPPORTED, "the tensor-core path serves the BLS12-381 scalar field only");
   ctx->matvec_path = path;
   return HBG_OK;
 }
@@ -947,26 +1084,37 @@ int hbg_vandermonde_batch_evaluate(hbg_ctx* ctx, const uint64_t* xs, int n, cons
   if (!out || (d && !polys)) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
   CU(cudaSetDevice(ctx->device));
   { int trc = cache_trim(ctx); if (trc) return trc; }
+  // V[i][j] = x_i^j, row-major, Montgomery form (set_vm_matrix, rsdecode_impl.h:23-36)
+  auto gen = [&](std::vector<Fe>& m) {
+    std::vector<Fe> x;
+    int r = load_points(ctx, xs, n, x);
+    if (r) return r;
+    m.assign((size_t)n * (d ? d : 1), fe_zero());
+    for (int i = 0; i < n; i++) {
+      Fe acc = ctx->field->one();
+      for (int j = 0; j < d; j++) {
+        m[(size_t)i * d + j] = acc;
+        acc = ctx->field->mul(acc, x[i]);
+      }
+    }
+    return HBG_OK;
+  };
+  const std::string key = make_key("vdm", xs, (size_t)n * 32, nullptr, 0, n, d);
+  TcPlan pl;
+  const bool tc = d > 0 && tc_wanted(ctx, n, d, batch, &pl);
   const void* d_m = nullptr;
-  int rc = get_const(ctx, make_key("vdm", xs, (size_t)n * 32, nullptr, 0, n, d), &d_m,
-                     [&](std::vector<uint32_t>& host) {
-                       std::vector<Fe> x;
-                       int r = load_points(ctx, xs, n, x);
-                       if (r) return r;
-                       std::vector<Fe> m((size_t)n * (d ? d : 1), fe_zero());
-                       for (int i = 0; i < n; i++) {  // set_vm_matrix, rsdecode_impl.h:23-36
-                         Fe acc = ctx->field->one();
-                         for (int j = 0; j < d; j++) {
-                           m[(size_t)i * d + j] = acc;
-                           acc = ctx->field->mul(acc, x[i]);
-                         }
-                       }
-                       interleave(m, n, d, host);
-                       return HBG_OK;
-                     });
+  int rc = tc ? tc_const(ctx, key, n, d, pl, &d_m, gen)
+              : get_const(ctx, key, &d_m, [&](std::vector<uint32_t>& host) {
+                  std::vector<Fe> m;
+                  int r = gen(m);
+                  if (r) return r;
+                  interleave(m, n, d, host);
+                  return HBG_OK;
+                });
   if (rc) return rc;
   return run_rows(ctx, polys, (size_t)d * 32, out, (size_t)n * 32, batch, mem,
                   [&](const void* di, void* dout, size_t rows) {
+                    if (tc) return launch_tc(ctx, d_m, pl, n, d, di, (size_t)d * 32, dout, (size_t)n * 32, rows);
                     return launch_matvec(ctx, d_m, n, d, di, d, dout, n, rows);
                   });
 }
@@ -985,8 +1133,21 @@ int hbg_vandermonde_batch_interpolate(hbg_ctx* ctx, const uint64_t* xs, int k, c
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
   if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  TcPlan pl;
+  const bool tc = tc_wanted(ctx, k, k, batch, &pl);
+  const void* d_b = nullptr;
+  if (tc) {
+    rc = tc_const(ctx, key, k, k, pl, &d_b, [&](std::vector<Fe>& inv) {
+      std::vector<Fe> x;
+      int r = load_points(ctx, xs, k, x);
+      if (r) return r;
+      return vandermonde_inverse(*ctx->field, x, inv) ? HBG_OK : HBG_ERR_SINGULAR;
+    });
+    if (rc) return rc;
+  }
   return run_rows(ctx, ys, (size_t)k * 32, out, (size_t)k * 32, batch, mem,
                   [&](const void* di, void* dout, size_t rows) {
+                    if (tc) return launch_tc(ctx, d_b, pl, k, k, di, (size_t)k * 32, dout, (size_t)k * 32, rows);
                     return launch_interp(ctx, key, d_m, k, di, dout, rows);
                   });
 }
@@ -1024,7 +1185,12 @@ int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], i
   if (!ctx) return HBG_ERR_INVALID;
   if (!omega || k < 1 || !zs || !ys || !peer_out || world < 1 || world > 8 || rank < 0 || rank >= world)
     return fail(ctx, HBG_ERR_INVALID, "bad argument");
-  if (k > 8) return fail(ctx, HBG_ERR_UNSUPPORTED, "fused all-gather is implemented for k <= 8");
+  TcPlan pl;
+  const bool tc = tc_wanted(ctx, k, k, batch, &pl);
+  if (k > 8 && !tc)
+    return fail(ctx, HBG_ERR_UNSUPPORTED,
+                "fused all-gather: k <= 8, or a shape the tensor-core kernel serves (BLS12-381 field, "
+                "constant operand resident in shared memory)");
   CU(cudaSetDevice(ctx->device));
   { int trc = cache_trim(ctx); if (trc) return trc; }
   const void* d_m = nullptr;
@@ -1044,8 +1210,6 @@ int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], i
                          });
   if (rc) return rc;
   if (batch == 0) return HBG_OK;
-  auto it = ctx->host_cache.find(key);
-  if (it == ctx->host_cache.end()) return fail(ctx, HBG_ERR_UNSUPPORTED, "matrix not cached on host");
   GatherDst g;
   memset(&g, 0, sizeof(g));
   g.world = world;
@@ -1054,6 +1218,22 @@ int hbg_fft_batch_interpolate_allgather(hbg_ctx* ctx, const uint64_t omega[4], i
     if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
     g.peers[r] = (uint4*)peer_out[r];
   }
+  if (tc) {  // tensor-core kernel, results stored from its epilogue into every rank's buffer
+    const void* d_b = nullptr;
+    rc = tc_const(ctx, key, k, k, pl, &d_b, [&](std::vector<Fe>& inv) {
+      Fe w;
+      int r = check_omega(ctx, omega, n, w);
+      if (r) return r;
+      std::vector<Fe> x(k);
+      for (int i = 0; i < k; i++) x[i] = ctx->field->pow_u64(w, (uint64_t)zs[i]);
+      return vandermonde_inverse(*ctx->field, x, inv) ? HBG_OK : HBG_ERR_SINGULAR;
+    });
+    if (rc) return rc;
+    return launch_tc(ctx, d_b, pl, k, k, ys, (size_t)k * 32, nullptr, (size_t)k * 32, batch, &g,
+                     (size_t)rank * batch);
+  }
+  auto it = ctx->host_cache.find(key);
+  if (it == ctx->host_cache.end()) return fail(ctx, HBG_ERR_UNSUPPORTED, "matrix not cached on host");
   rc = bind_field(ctx);
   if (rc) return rc;
   rc = ctx->is_bls ? launch_interp_small_f<FieldBLS>(ctx, k, it->second, ys, nullptr, batch, &g,
@@ -1089,34 +1269,49 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   if (ctx->fft_path == 1 && (size_t)k_out * d_eff <= (1u << 22)) use_matrix = true;
   if (ctx->fft_path >= 2 && n >= 2) use_matrix = false;
   if ((size_t)k_out * d_eff > (1u << 22)) use_matrix = false;
+  // the matrix form on the tensor cores beats both whenever its constant operand fits
+  TcPlan pl;
+  const bool tc = d_eff > 0 && (ctx->fft_path <= 1 || n < 2) && tc_wanted(ctx, k_out, d_eff, batch, &pl);
+  if (tc) use_matrix = true;
   const void* d_m = nullptr;
   const void* d_tw = nullptr;
   const std::vector<uint32_t>* h_tw = nullptr;
   if (use_matrix) {
-    rc = get_const(ctx, make_key("dft", omega, 32, &n, sizeof n, k_out, d_eff), &d_m,
-                   [&](std::vector<uint32_t>& host) {
-                     Fe w;
-                     int r = check_omega(ctx, omega, n, w);
-                     if (r) return r;
-                     std::vector<Fe> m((size_t)k_out * (d_eff ? d_eff : 1), fe_zero());
-                     Fe wi = ctx->field->one();  // omega^i
-                     for (int i = 0; i < k_out; i++) {
-                       Fe acc = ctx->field->one();
-                       for (int j = 0; j < d_eff; j++) {
-                         m[(size_t)i * d_eff + j] = acc;
-                         acc = ctx->field->mul(acc, wi);
-                       }
-                       wi = ctx->field->mul(wi, w);
-                     }
-                     interleave(m, k_out, d_eff, host);
-                     return HBG_OK;
-                   });
+    // M[i][j] = omega^(i j), row-major, Montgomery form
+    auto gen = [&](std::vector<Fe>& m) {
+      Fe w;
+      int r = check_omega(ctx, omega, n, w);
+      if (r) return r;
+      m.assign((size_t)k_out * (d_eff ? d_eff : 1), fe_zero());
+      Fe wi = ctx->field->one();  // omega^i
+      for (int i = 0; i < k_out; i++) {
+        Fe acc = ctx->field->one();
+        for (int j = 0; j < d_eff; j++) {
+          m[(size_t)i * d_eff + j] = acc;
+          acc = ctx->field->mul(acc, wi);
+        }
+        wi = ctx->field->mul(wi, w);
+      }
+      return HBG_OK;
+    };
+    const std::string key = make_key("dft", omega, 32, &n, sizeof n, k_out, d_eff);
+    rc = tc ? tc_const(ctx, key, k_out, d_eff, pl, &d_m, gen)
+            : get_const(ctx, key, &d_m, [&](std::vector<uint32_t>& host) {
+                std::vector<Fe> m;
+                int r = gen(m);
+                if (r) return r;
+                interleave(m, k_out, d_eff, host);
+                return HBG_OK;
+              });
   } else {
     rc = twiddles(ctx, omega, n, &d_tw, &h_tw);
   }
   if (rc) return rc;
   return run_rows(ctx, polys, (size_t)d * 32, out, (size_t)k_out * 32, batch, mem,
                   [&](const void* di, void* dout, size_t rows) {
+                    if (tc)
+                      return launch_tc(ctx, d_m, pl, k_out, d_eff, di, (size_t)d * 32, dout,
+                                       (size_t)k_out * 32, rows);
                     if (use_matrix) return launch_matvec(ctx, d_m, k_out, d_eff, di, d, dout, k_out, rows);
                     return launch_ntt(ctx, d_tw, h_tw, n, di, d, dout, k_out, rows);
                   });
@@ -1147,9 +1342,141 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
   if (rc) return rc;
   if (batch == 0 || k == 0) return HBG_OK;
   if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  TcPlan pl;
+  const bool tc = tc_wanted(ctx, k, k, batch, &pl);
+  const void* d_b = nullptr;
+  if (tc) {
+    rc = tc_const(ctx, key, k, k, pl, &d_b, [&](std::vector<Fe>& inv) {
+      Fe w;
+      int r = check_omega(ctx, omega, n, w);
+      if (r) return r;
+      std::vector<Fe> x(k);
+      for (int i = 0; i < k; i++) x[i] = ctx->field->pow_u64(w, (uint64_t)zs[i]);
+      return vandermonde_inverse(*ctx->field, x, inv) ? HBG_OK : HBG_ERR_SINGULAR;
+    });
+    if (rc) return rc;
+  }
   return run_rows(ctx, ys, (size_t)k * 32, out, (size_t)k * 32, batch, mem,
                   [&](const void* di, void* dout, size_t rows) {
+                    if (tc) return launch_tc(ctx, d_b, pl, k, k, di, (size_t)k * 32, dout, (size_t)k * 32, rows);
                     return launch_interp(ctx, key, d_m, k, di, dout, rows);
+                  });
+}
+
+int hbg_ctx_set_cache_limit(hbg_ctx* ctx, size_t bytes) {
+  if (!ctx) return HBG_ERR_INVALID;
+  ctx->cache_limit = bytes;
+  return HBG_OK;
+}
+
+int hbg_columns_to_rows(hbg_ctx* ctx, const uint64_t* colbuf, size_t batch, const int32_t* idx, int k,
+                        uint64_t* rows) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (k < 0 || k > 256 || (k && !idx)) return fail(ctx, HBG_ERR_INVALID, "0 <= k <= 256 columns");
+  if (batch == 0 || k == 0) return HBG_OK;
+  if (!colbuf || !rows) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  CU(cudaSetDevice(ctx->device));
+  ColumnIdx ci;
+  memset(&ci, 0, sizeof ci);
+  for (int j = 0; j < k; j++) {
+    if (idx[j] < 0) return fail(ctx, HBG_ERR_INVALID, "negative column index");
+    ci.idx[j] = idx[j];
+  }
+  unsigned long long blocks = (batch * (unsigned long long)k + 255) / 256;
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  columns_to_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)colbuf, batch, ci, k,
+                                                                     (uint4*)rows);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "columns_to_rows_kernel";
+  return HBG_OK;
+}
+
+int hbg_compare_columns(hbg_ctx* ctx, const uint64_t* rows, int row_width, int col_offset,
+                        const uint64_t* colbuf, size_t batch, const int32_t* idx, int m, int32_t* flags_dev,
+                        int32_t* flags_host) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (m < 0 || m > 256 || (m && !idx) || row_width < 1 || col_offset < 0)
+    return fail(ctx, HBG_ERR_INVALID, "bad size (0 <= m <= 256 columns)");
+  if (m == 0) return HBG_OK;
+  if (!flags_dev) return fail(ctx, HBG_ERR_INVALID, "null flags buffer");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(flags_dev, 0, (size_t)m * 4, ctx->stream));
+  if (batch) {
+    if (!rows || !colbuf) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+    ColumnIdx ci;
+    memset(&ci, 0, sizeof ci);
+    for (int j = 0; j < m; j++) {
+      if (idx[j] < 0 || col_offset + idx[j] >= row_width)
+        return fail(ctx, HBG_ERR_INVALID, "column index outside the row");
+      ci.idx[j] = idx[j];
+    }
+    unsigned long long blocks = (batch * (unsigned long long)m + 255) / 256;
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    compare_columns_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+        (const uint4*)rows, row_width, col_offset, (const uint4*)colbuf, batch, ci, m, flags_dev);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_kernel = "compare_columns_kernel";
+  }
+  if (flags_host) {
+    CU(cudaMemcpyAsync(flags_host, flags_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return HBG_OK;
+}
+
+int hbg_interpolate_reencode(hbg_ctx* ctx, const uint64_t* xs_k, int k, const uint64_t* xs_all, int n,
+                             const uint64_t* ys, size_t batch, uint64_t* out, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (k < 1 || n < 0 || !xs_k || (n && !xs_all)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
+  // the stacked matrix [W ; V(xs_all) W], W = V(xs_k)^-1, row-major, Montgomery form
+  auto gen = [&](std::vector<Fe>& m) {
+    std::vector<Fe> xk, xa, inv;
+    int r = load_points(ctx, xs_k, k, xk);
+    if (r) return r;
+    r = load_points(ctx, xs_all, n, xa);
+    if (r) return r;
+    if (!vandermonde_inverse(*ctx->field, xk, inv))
+      return fail(ctx, HBG_ERR_SINGULAR, "evaluation points are not pairwise distinct");
+    const HostField& f = *ctx->field;
+    m.assign((size_t)(k + n) * k, fe_zero());
+    for (int i = 0; i < k * k; i++) m[i] = inv[i];
+    for (int i = 0; i < n; i++) {  // row i of V(xs_all) W by Horner over the rows of W
+      for (int j = 0; j < k; j++) {
+        Fe acc = inv[(size_t)(k - 1) * k + j];
+        for (int l = k - 2; l >= 0; l--) acc = f.add(f.mul(acc, xa[i]), inv[(size_t)l * k + j]);
+        m[(size_t)(k + i) * k + j] = acc;
+      }
+    }
+    return HBG_OK;
+  };
+  const int n_out = k + n;
+  std::string key = make_key("ireenc", xs_k, (size_t)k * 32, xs_all, (size_t)n * 32, k, n);
+  TcPlan pl;
+  const bool tc = tc_wanted(ctx, n_out, k, batch, &pl);
+  const void* d_m = nullptr;
+  int rc = tc ? tc_const(ctx, key, n_out, k, pl, &d_m, gen)
+              : get_const(ctx, key, &d_m, [&](std::vector<uint32_t>& host) {
+                  std::vector<Fe> m;
+                  int r = gen(m);
+                  if (r) return r;
+                  interleave(m, n_out, k, host);
+                  return HBG_OK;
+                });
+  if (rc) return rc;
+  if (batch == 0) return HBG_OK;
+  if (!ys || !out) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  return run_rows(ctx, ys, (size_t)k * 32, out, (size_t)n_out * 32, batch, mem,
+                  [&](const void* di, void* dout, size_t rows) {
+                    if (tc)
+                      return launch_tc(ctx, d_m, pl, n_out, k, di, (size_t)k * 32, dout, (size_t)n_out * 32,
+                                       rows);
+                    return launch_matvec(ctx, d_m, n_out, k, di, k, dout, n_out, rows);
                   });
 }
 

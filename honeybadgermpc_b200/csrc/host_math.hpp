@@ -78,6 +78,35 @@ inline bool field_params_init(const uint64_t p64[4], FieldParams* fp) {
   return true;
 }
 
+// floor(2^280 / p) for 2^248 < p < 2^256 (the small-quotient Barrett constant of
+// tc_kernels.cuh: tc_fold_reduce); 0 when it does not fit 32 bits.
+inline uint32_t barrett_mu280(const FieldParams& fp) {
+  uint32_t rem[9] = {0};
+  unsigned long long q = 0;
+  for (int bit = 280; bit >= 0; bit--) {  // long division of 2^280, bit by bit
+    uint32_t carry = bit == 280 ? 1u : 0u;
+    for (int w = 0; w < 9; w++) {
+      const uint32_t nc = rem[w] >> 31;
+      rem[w] = (rem[w] << 1) | carry;
+      carry = nc;
+    }
+    uint32_t t[9];
+    long long b = 0;
+    for (int w = 0; w < 9; w++) {
+      const long long dd = (long long)rem[w] - (long long)(w < 8 ? fp.p[w] : 0u) + b;
+      t[w] = (uint32_t)dd;
+      b = dd >> 32;
+    }
+    q <<= 1;
+    if (b == 0) {
+      memcpy(rem, t, sizeof t);
+      q |= 1;
+    }
+    if (q >> 32) return 0;
+  }
+  return (uint32_t)q;
+}
+
 // A field bound to its parameters; all values held by users of this class are
 // in MONTGOMERY form unless a name says "std".
 class HostField {

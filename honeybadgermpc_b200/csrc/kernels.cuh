@@ -283,6 +283,49 @@ __global__ void __launch_bounds__(256) gather_copy_kernel(const uint4* src, Gath
   }
 }
 
+// ---------------------------------------------------------------------------
+// device-resident IncrementalDecoder (reed_solomon.py:305-331): columns live as
+// colbuf[n][batch]; these two kernels are pure data movement / comparison.
+// ---------------------------------------------------------------------------
+struct ColumnIdx {
+  int idx[256];
+};
+
+// rows[b][j] = colbuf[idx[j]][b]: thread = (row, column), 32 bytes each way; a warp reads
+// 32 consecutive elements of one column (coalesced) when k divides the warp evenly or not.
+__global__ void __launch_bounds__(256) columns_to_rows_kernel(const uint4* colbuf, unsigned long long batch,
+                                                              ColumnIdx ci, int k, uint4* rows) {
+  const unsigned long long total = batch * (unsigned)k;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * 256) {
+    const unsigned j = (unsigned)(t / batch);       // column-major sweep: coalesced reads
+    const unsigned long long b = t - (unsigned long long)j * batch;
+    const uint4* src = colbuf + 2ull * ((unsigned long long)ci.idx[j] * batch + b);
+    uint4* dst = rows + 2ull * (b * (unsigned)k + j);
+    dst[0] = src[0];
+    dst[1] = src[1];
+  }
+}
+
+// flags[j] = 1 when column idx[j] differs anywhere from rows[.][col_offset + idx[j]]
+__global__ void __launch_bounds__(256) compare_columns_kernel(const uint4* rows, int row_width, int col_offset,
+                                                              const uint4* colbuf, unsigned long long batch,
+                                                              ColumnIdx ci, int m, int* flags) {
+  const unsigned long long total = batch * (unsigned)m;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * 256) {
+    const unsigned j = (unsigned)(t / batch);
+    const unsigned long long b = t - (unsigned long long)j * batch;
+    const int col = ci.idx[j];
+    const uint4* x = colbuf + 2ull * ((unsigned long long)col * batch + b);
+    const uint4* y = rows + 2ull * (b * (unsigned)row_width + (unsigned)(col_offset + col));
+    const uint4 x0 = x[0], x1 = x[1], y0 = y[0], y1 = y[1];
+    const bool same = x0.x == y0.x && x0.y == y0.y && x0.z == y0.z && x0.w == y0.w && x1.x == y1.x &&
+                      x1.y == y1.y && x1.z == y1.z && x1.w == y1.w;
+    if (!same) flags[j] = 1;
+  }
+}
+
 // within the 8-point transform: after s stages slot idx depends on the inputs
 // j = idx (mod 8 >> s); with the first D8 inputs non-zero it is non-zero iff that
 // residue is < D8

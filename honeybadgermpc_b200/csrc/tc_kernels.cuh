@@ -1,0 +1,458 @@
+// Constant-matrix products on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   out[b][i] = sum_j M[i][j] * in[b][j]  (mod p),   M fixed for the whole batch
+//
+// is what every non-robust primitive of the reconstruction path computes
+// (vandermonde_batch_evaluate / _interpolate, fft_batch_interpolate and the matrix
+// form of fft_batch_evaluate: rsdecode_impl.h:23-36, :97-122, :125-192, pyx:183,237).
+// The IMAD kernels (kernels.cuh) spend 64 IMAD.WIDE per 256-bit product and are bound
+// by the integer multiplier.  Here the products run as an EXACT unsigned 8-bit integer
+// GEMM with 32-bit accumulation:
+//
+//   * a field element is 32 bytes; row b of the batch is already a K = 32*d byte
+//     vector A[b][(j,a)] = byte a of in[b][j]           -- the HBM layout as it is;
+//   * the constant operand absorbs the modular reduction:
+//         B[(i,c)][(j,a)] = byte c of ( M[i][j] * 2^(8a) mod p ),
+//     because in[b][j] = sum_a A[b][(j,a)] 2^(8a), so
+//         V[b][i] := sum_c 2^(8c) * ( sum_(j,a) A[b][(j,a)] * B[(i,c)][(j,a)] )
+//                 == out[b][i]  (mod p),     V < 2^280 for d <= 1032;
+//   * D = A * B^T is one tcgen05.mma.kind::i8 chain per 128-row tile (u8 x u8 -> s32 in
+//     TMEM); the epilogue reads each output's 32 column sums with tcgen05.ld, carries
+//     them into a 288-bit integer and reduces it with one small-quotient Barrett step
+//     (q < 2^26: 8 IMAD.WIDE) and one conditional subtraction.  No Montgomery form
+//     anywhere: inputs, constants and outputs are plain residues.
+//
+// Warp roles of the persistent CTA (one per SM): EW = 8, 12 or 16 epilogue warps (TMEM
+// lane quarter = warp % 4, the outputs of a block dealt round-robin over warp / 4), one
+// thread streams the 128-row A tiles into a ring of shared-memory stages with TMA tensor
+// copies (128-byte-wide boxes, SWIZZLE_128B = the UMMA K-major swizzled layout; rows past the
+// batch and bytes past K are zero-filled by the TMA unit; measured: 16-byte cp.async copies
+// from 128 threads could not keep more than ~2 TB/s of loads in flight), one warp owns
+// TMEM and issues the MMAs
+// (one elected thread).  The constant operand is fetched once per CTA by one TMA bulk
+// copy and stays resident in shared memory; accumulators ping-pong between two
+// 256-column TMEM buffers so the MMAs of one block overlap the epilogue of the previous.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fp256.cuh"
+
+namespace hb {
+
+struct TcArgs {
+  const uint8_t* in;         // rows of K bytes, pitch in_pitch bytes (multiple of 16)
+  const uint8_t* bmat;       // n_blocks blocks of (32*ob) x K bytes, UMMA canonical K-major layout
+  uint8_t* out;              // output o of row r at r*out_pitch + o*32
+  unsigned long long batch;
+  unsigned K;                // 32 * d
+  unsigned n_out;            // outputs per row
+  unsigned ob;               // outputs per accumulator block (1..8)
+  unsigned n_blocks;         // ceil(n_out / ob)
+  unsigned in_pitch, out_pitch;
+  unsigned stages;           // A stages in shared memory (>= 2); one stage = ceil(K/128) boxes of 16 KB
+  unsigned mu;               // floor(2^280 / p)
+  // fused all-gather (hbg_fft_batch_interpolate_allgather): when gather_world > 0 the result of
+  // row r is stored at row gather_row0 + r of EVERY rank's buffer -- one multimem.st per 16
+  // bytes through the NVSwitch multicast address gather_mc, or gather_world peer stores
+  uint8_t* gather_peers[8];
+  uint8_t* gather_mc;
+  unsigned long long gather_row0;
+  unsigned gather_world;
+  unsigned hyp;              // probe only: descriptor field hypotheses
+  uint32_t* debug;           // probe only: raw column sums of the first tile, or null
+  long long* trace;          // probe only: clock64 stamps of CTA 0, [role][tile < 64][event < 8]
+  unsigned* error;           // set to non-zero when a barrier wait times out
+};
+
+constexpr int kTcMaxStages = 6;
+constexpr int kTcLoadWarps = 1;  // one elected thread issues the TMA tensor copies
+
+HB_D unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+HB_D void tc_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+
+HB_D void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+// Bounded wait: a protocol bug must end in an error code, not in a hung GPU.
+HB_D bool tc_mbar_wait(uint64_t* bar, unsigned parity, unsigned* error) {
+  const unsigned a = tc_smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s
+      if (error) atomicExch(error, 1u);
+      __trap();
+    }
+  }
+}
+
+HB_D uint64_t tc_smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+  // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46),
+  // version 1 [46,48), layout type 0 = no swizzle [61,64)
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+
+// K-major operand in the 128-byte-swizzled layout TMA writes (rows of 128 bytes, 8-row groups
+// of 1024 bytes): layout type 2, SBO = 1024, LBO unused (1).  A K step of 32 bytes advances
+// the start address inside the swizzle span.
+HB_D uint64_t tc_smem_desc_sw128(unsigned addr) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+HB_D void tc_mma_i8(unsigned d_tmem, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+HB_D void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   tc_smem_u32(bar))
+               : "memory");
+}
+
+HB_D void tc_ld32(unsigned taddr, uint32_t* c) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]),
+        "=r"(c[8]), "=r"(c[9]), "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]),
+        "=r"(c[15]), "=r"(c[16]), "=r"(c[17]), "=r"(c[18]), "=r"(c[19]), "=r"(c[20]), "=r"(c[21]),
+        "=r"(c[22]), "=r"(c[23]), "=r"(c[24]), "=r"(c[25]), "=r"(c[26]), "=r"(c[27]), "=r"(c[28]),
+        "=r"(c[29]), "=r"(c[30]), "=r"(c[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 column sums (weights 2^(8c), each < 2^31) -> the canonical residue of
+// V = sum_c col[c] 2^(8c) modulo p, for V < 2^279.
+//   1. eight independent 64-bit word sums s_i = c[4i] + c[4i+1] 2^8 + c[4i+2] 2^16 + c[4i+3] 2^24
+//      (three IMAD.WIDE each, no dependency between words), one 32-bit carry chain -> w[0..8];
+//   2. q = floor(floor(V / 2^248) * mu / 2^32) with mu = floor(2^280 / p): q <= V/p and
+//      V/p - q < 1 + V/2^280 + 2^248/p < 2, so R = V - q p lies in [0, 2p) and fits 256 bits;
+//   3. R is computed modulo 2^256 (eight independent q*p_i products, two carry chains) and
+//      reduced with ONE conditional subtraction of p.
+template <class F>
+HB_D void tc_fold_reduce(const uint32_t* c, uint32_t mu, Fe& r) {
+  uint32_t lo[8], hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    unsigned long long s = (unsigned long long)c[4 * i + 1] * 256u + c[4 * i];
+    s += (unsigned long long)c[4 * i + 2] * 65536u;
+    s += (unsigned long long)c[4 * i + 3] * 16777216u;
+    lo[i] = (uint32_t)s;
+    hi[i] = (uint32_t)(s >> 32);
+  }
+  uint32_t w[9];
+  w[0] = lo[0];
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8])
+      : "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(hi[7]),
+        "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]));
+  const uint32_t top = __funnelshift_l(w[7], w[8], 8);  // floor(V / 2^248)
+  const uint32_t q = __umulhi(top, mu);
+  // q*p modulo 2^256: even-limb products on aligned word pairs, odd-limb products one word up
+  uint32_t e[8], o[8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned long long pe = (unsigned long long)q * F::p(2 * j);
+    e[2 * j] = (uint32_t)pe;
+    e[2 * j + 1] = (uint32_t)(pe >> 32);
+    const unsigned long long po = (unsigned long long)q * F::p(2 * j + 1);
+    o[2 * j] = (uint32_t)po;
+    o[2 * j + 1] = (uint32_t)(po >> 32);
+  }
+  // R = w - e - (o << 32)   (mod 2^256)
+  uint32_t t[8];
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+      : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
+        "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]));
+  asm("sub.cc.u32 %0, %0, %7;\n\t"
+      "subc.cc.u32 %1, %1, %8;\n\t"
+      "subc.cc.u32 %2, %2, %9;\n\t"
+      "subc.cc.u32 %3, %3, %10;\n\t"
+      "subc.cc.u32 %4, %4, %11;\n\t"
+      "subc.cc.u32 %5, %5, %12;\n\t"
+      "subc.u32 %6, %6, %13;"
+      : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7])
+      : "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]));
+  // one conditional subtraction of p
+  uint32_t u[8], borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(borrow)
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "r"(F::p(0)), "r"(F::p(1)), "r"(F::p(2)), "r"(F::p(3)), "r"(F::p(4)), "r"(F::p(5)), "r"(F::p(6)),
+        "r"(F::p(7)));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.w[i] = borrow ? t[i] : u[i];
+}
+
+HB_D void tc_st256(uint8_t* p, const Fe& r) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]),
+               "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+               : "memory");
+}
+
+HB_D void tc_st_multimem(uint8_t* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("multimem.st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+
+#define TC_TRACE(role, it_, ev)                                                              \
+  do {                                                                                       \
+    if (a.trace && blockIdx.x == 0 && (it_) < 64) a.trace[((role)*64 + (it_)) * 8 + (ev)] = clock64(); \
+  } while (0)
+
+template <class F, int EW>
+__global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  constexpr int kTcEpiWarps = EW;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_tfull[2], bar_tempty[2], bar_b;
+  __shared__ unsigned tmem_base_slot;
+
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned NB = 32 * a.ob;            // accumulator columns per block
+  const unsigned KBOX = (a.K + 127) >> 7;   // 128-byte-wide TMA boxes per tile
+  const unsigned KS = a.K >> 5;             // MMA K steps (32 bytes each)
+  const unsigned b_block_bytes = NB * a.K;
+  const unsigned b_bytes = b_block_bytes * a.n_blocks;
+  const unsigned stage_bytes = KBOX * 16384;
+  uint8_t* smem_b = tc_smem;
+  uint8_t* smem_a = tc_smem + ((b_bytes + 1023) & ~1023u);  // swizzle atoms need 1024-byte alignment
+  const unsigned long long tiles = (a.batch + 127) >> 7;
+
+  // --- set-up: barriers, TMEM, the resident constant operand -------------------
+  if (threadIdx.x == 0) {
+    for (unsigned s = 0; s < a.stages; s++) {
+      tc_mbar_init(&bar_full[s], 1);
+      tc_mbar_init(&bar_empty[s], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      tc_mbar_init(&bar_tfull[i], 1);
+      tc_mbar_init(&bar_tempty[i], kTcEpiWarps);
+    }
+    tc_mbar_init(&bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the constant operand: one TMA bulk copy (written by the async proxy, read by the MMAs)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&bar_b)),
+                 "r"(b_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            tc_smem_u32(smem_b)),
+        "l"(a.bmat), "r"(b_bytes), "r"(tc_smem_u32(&bar_b))
+        : "memory");
+  }
+  if (warp == kTcEpiWarps + kTcLoadWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                     tc_smem_u32(&tmem_base_slot))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_base = tmem_base_slot;
+
+  if (warp == kTcEpiWarps) {
+    // ===== loader: one thread, ceil(K/128) TMA box copies per tile, `stages` tiles in flight =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      unsigned it = 0;
+      for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+        const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
+        tc_mbar_wait(&bar_empty[s], ph ^ 1, a.error);
+        TC_TRACE(0, it, 0);
+        const unsigned bar = tc_smem_u32(&bar_full[s]);
+        if (a.hyp & 8) {  // probe: no loads
+          tc_mbar_arrive(&bar_full[s]);
+          continue;
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes)
+                     : "memory");
+        const unsigned dst = tc_smem_u32(smem_a + (size_t)s * stage_bytes);
+        const int row0 = (int)(tile << 7);
+        for (unsigned kb = 0; kb < KBOX; kb++)
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst + kb * 16384),
+              "l"(&tmap), "r"((int)(kb * 128)), "r"(row0), "r"(bar)
+              : "memory");
+        TC_TRACE(0, it, 1);
+      }
+    }
+  } else if (warp == kTcEpiWarps + kTcLoadWarps) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a/b format UINT8 (0), K-major both,
+      // N >> 3 at [17,23), M >> 4 at [24,29)
+      const unsigned idesc = (2u << 4) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
+      const unsigned b_lbo = NB * 16, b_sbo = 128u;
+      unsigned it = 0, acc_it = 0;
+      tc_mbar_wait(&bar_b, 0, a.error);
+      for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+        const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
+        tc_mbar_wait(&bar_full[s], ph, a.error);
+        TC_TRACE(1, it, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned a_base = tc_smem_u32(smem_a + (size_t)s * stage_bytes);
+        for (unsigned nb = 0; nb < a.n_blocks; nb++, acc_it++) {
+          const unsigned buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+          tc_mbar_wait(&bar_tempty[buf], aph ^ 1, a.error);
+          if (nb == 0) TC_TRACE(1, it, 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned b_base = tc_smem_u32(smem_b + (size_t)nb * b_block_bytes);
+          for (unsigned ks = 0; ks < KS && !(a.hyp & 16); ks++) {
+            const uint64_t ad = tc_smem_desc_sw128(a_base + (ks >> 2) * 16384 + (ks & 3) * 32);
+            const uint64_t bd = tc_smem_desc(b_base + ks * 2 * (NB * 16), b_lbo, b_sbo);
+            tc_mma_i8(tmem_base + buf * 256, ad, bd, idesc, ks > 0);
+          }
+          tc_commit(&bar_tfull[buf]);
+        }
+        tc_commit(&bar_empty[s]);
+        TC_TRACE(1, it, 2);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = row (TMEM lane); warp / 4 deals out the outputs of a block =====
+    const unsigned quarter = warp & 3, group = warp >> 2;
+    unsigned it = 0, acc_it = 0;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+      const unsigned long long row = (tile << 7) + quarter * 32 + lane;
+      for (unsigned nb = 0; nb < a.n_blocks; nb++, acc_it++) {
+        const unsigned buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        tc_mbar_wait(&bar_tfull[buf], aph, a.error);
+        if (threadIdx.x == 0 && nb == 0) TC_TRACE(2, it, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (unsigned o = group; o < a.ob; o += kTcEpiWarps / 4) {
+          uint32_t c[32];
+          if (a.hyp & 4) continue;  // probe: no TMEM read, no arithmetic, no store
+          tc_ld32(tmem_base + ((quarter * 32) << 16) + buf * 256 + o * 32, c);
+          if (a.hyp & 2) {          // probe: TMEM read only
+            if (c[0] == 0xdeadbeefu && c[31] == 0x12345u) a.out[0] = 1;
+            continue;
+          }
+          const unsigned out_idx = nb * a.ob + o;
+          if (a.debug) {
+            if (tile == 0 && row < 128)
+              for (int i = 0; i < 32; i++) a.debug[(row * a.n_blocks * NB) + nb * NB + o * 32 + i] = c[i];
+          }
+          if (row < a.batch && out_idx < a.n_out) {
+            Fe r;
+            tc_fold_reduce<F>(c, a.mu, r);
+            if (a.gather_world == 0) {
+              tc_st256(a.out + row * a.out_pitch + out_idx * 32, r);
+            } else {
+              const unsigned long long off = (a.gather_row0 + row) * a.out_pitch + out_idx * 32;
+              if (a.gather_mc) {
+                tc_st_multimem(a.gather_mc + off, r.w[0], r.w[1], r.w[2], r.w[3]);
+                tc_st_multimem(a.gather_mc + off + 16, r.w[4], r.w[5], r.w[6], r.w[7]);
+              } else {
+                for (unsigned w = 0; w < a.gather_world; w++) tc_st256(a.gather_peers[w] + off, r);
+              }
+            }
+          }
+        }
+        if (threadIdx.x == 0 && nb == 0) TC_TRACE(2, it, 1);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&bar_tempty[buf]);
+        if (threadIdx.x == 0 && nb == 0) TC_TRACE(2, it, 2);
+      }
+    }
+  }
+
+  // --- teardown -----------------------------------------------------------------
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kTcEpiWarps + kTcLoadWarps) {
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// Host: the TMA descriptor of the input rows -- a 2-D u8 tensor (K bytes x batch rows, row pitch
+// in_pitch), boxes of 128 bytes x 128 rows written to shared memory with the 128-byte swizzle.
+// cuTensorMapEncodeTiled is a pure host routine of the driver; it is looked up through the
+// runtime so that the library does not link libcuda.
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+
+inline bool tc_make_tmap(CUtensorMap* m, const void* in, unsigned long long batch, unsigned K,
+                         unsigned long long in_pitch) {
+  static tc_encode_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (tc_encode_fn)p;
+  }();
+  if (!fn || ((uintptr_t)in & 15) || (in_pitch & 15)) return false;
+  const cuuint64_t dims[2] = {K, batch};
+  const cuuint64_t strides[1] = {in_pitch};
+  const cuuint32_t box[2] = {128, 128};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(in), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Host: shared memory the kernel needs for (K, n_blocks, ob, stages) -- plus up to 1008 bytes
+// the kernel may skip to align its dynamic shared memory window to 1024.
+inline size_t tc_stage_bytes(unsigned K) { return (size_t)((K + 127) / 128) * 16384; }
+inline size_t tc_smem_bytes(unsigned K, unsigned n_blocks, unsigned ob, unsigned stages) {
+  const size_t b_bytes = (size_t)32 * ob * K * n_blocks;
+  return ((b_bytes + 1023) & ~(size_t)1023) + (size_t)stages * tc_stage_bytes(K);
+}
+
+}  // namespace hb

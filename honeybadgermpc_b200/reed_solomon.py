@@ -10,8 +10,11 @@ What is different underneath:
   * every codec also has ``*_limbs`` methods working on ``uint64[batch, w, 4]``
     arrays, so a pipeline (decode -> re-encode -> compare) never goes through
     Python ints;
-  * ``IncrementalDecoder`` keeps the received columns as limb arrays, validates
-    later columns with one vectorised compare, and on the Byzantine path
+  * ``IncrementalDecoder`` keeps the received columns in DEVICE memory (one
+    ``colbuf[n][batch]`` buffer): the optimistic decode and the re-encode are one
+    fused kernel (``hbg_interpolate_reencode``), later columns are validated by
+    a compare kernel, and only per-column mismatch flags and the final rows come
+    back (``device=False``: the same logic on host limb arrays); on the Byzantine path it
     decodes ALL remaining rows in one batched kernel call per eviction round
     (``robust_decode_batch``) instead of one Python call per row
     (reed_solomon.py:334-365) -- same results, because rows are still accepted
@@ -261,6 +264,80 @@ class WelchBerlekampRobustDecoder(RobustDecoder):
 
 _GUESS = object()  # IncrementalDecoder._result: "the accepted optimistic guess, still as limbs"
 
+DEVICE_MIN_BATCH = 256  # below this the host path's few numpy ops beat kernel launches
+
+
+class _DeviceColumns:
+    """Device side of one IncrementalDecoder: the column buffer ``colbuf[n][batch]``, the
+    fused decode+re-encode output ``guess[batch][k+n]`` and the per-column mismatch flags.
+    torch is the memory / stream plumbing; the work is the three C-ABI calls
+    ``hbg_columns_to_rows``, ``hbg_interpolate_reencode``, ``hbg_compare_columns``."""
+
+    _stream = None
+    totals = {"decoders": 0, "c_abi_calls": 0, "h2d_bytes": 0, "d2h_bytes": 0}  # process-wide counters
+
+    def __init__(self, ctx, n, batch, k):
+        import torch
+
+        _DeviceColumns.totals["decoders"] += 1
+
+        self.torch, self.ctx, self.n, self.batch, self.k = torch, ctx, n, batch, k
+        self.dev = torch.device("cuda", ctx.device)
+        if _DeviceColumns._stream is None or _DeviceColumns._stream.device != self.dev:
+            _DeviceColumns._stream = torch.cuda.Stream(device=self.dev)
+        self.stream = _DeviceColumns._stream
+        ctx.set_stream(self.stream.cuda_stream)
+        with torch.cuda.stream(self.stream):
+            self.colbuf = torch.empty((n, batch, 4), dtype=torch.int64, device=self.dev)
+            self.guess = None
+            self.flags = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        self.compared = []   # party indices whose compare kernel has been enqueued
+
+    def put(self, idx, col):
+        """H2D of one received column (uint64[batch, 4])"""
+        t = self.torch
+        src = np.require(col, requirements=["C", "W"]).view(np.int64)  # frombuffer views are read-only
+        with t.cuda.stream(self.stream):
+            self.colbuf[idx].copy_(t.from_numpy(src), non_blocking=True)
+        _DeviceColumns.totals["h2d_bytes"] += col.nbytes
+
+    def decode_reencode(self, z, xs_k, xs_all):
+        t = self.torch
+        with t.cuda.stream(self.stream):
+            rows = t.empty((self.batch, self.k, 4), dtype=t.int64, device=self.dev)
+            self.guess = t.empty((self.batch, self.k + self.n, 4), dtype=t.int64, device=self.dev)
+        self.ctx.columns_to_rows(self.colbuf.data_ptr(), self.batch, z, rows.data_ptr())
+        self.ctx.interpolate_reencode(xs_k, xs_all, rows.data_ptr(), self.batch, self.guess.data_ptr(),
+                                      mem=ntl._native.MEM_DEVICE)
+        _DeviceColumns.totals["c_abi_calls"] += 2
+
+    def compare(self, idx):
+        """enqueue the validation of column idx against the re-encoded guess (no sync)"""
+        self.ctx.compare_columns(self.guess.data_ptr(), self.k + self.n, self.k, self.colbuf.data_ptr(),
+                                 self.batch, [idx], self.flags[idx:idx + 1].data_ptr())
+        self.compared.append(idx)
+        _DeviceColumns.totals["c_abi_calls"] += 1
+
+    def any_mismatch(self):
+        """one D2H of all flags written so far"""
+        if not self.compared:
+            return False
+        with self.torch.cuda.stream(self.stream):
+            host = self.flags.cpu()
+        _DeviceColumns.totals["d2h_bytes"] += host.numel() * 4
+        return bool(host[self.compared].any())
+
+    def coefficients(self):
+        """uint64[batch, k, 4] on the host"""
+        with self.torch.cuda.stream(self.stream):
+            out = self.guess[:, : self.k, :].contiguous().cpu().numpy().view(np.uint64)
+        _DeviceColumns.totals["d2h_bytes"] += out.nbytes
+        return out
+
+    def encoded_host(self):
+        with self.torch.cuda.stream(self.stream):
+            return self.guess[:, self.k:, :].contiguous().cpu().numpy().view(np.uint64)
+
 
 class IncrementalDecoder:
     """reed_solomon.py:232-403.  Feed it one party's column at a time with
@@ -271,11 +348,24 @@ class IncrementalDecoder:
     parties agree on every row."""
 
     def __init__(self, encoder, decoder, robust_decoder, degree, batch_size, max_errors,
-                 confirmed_errors=None, validator=None):
+                 confirmed_errors=None, validator=None, device="auto"):
         self.encoder, self.decoder, self.robust_decoder = encoder, decoder, robust_decoder
         self.degree, self.batch_size, self.max_errors = degree, batch_size, max_errors
         self.validator = validator
         self.modulus = encoder.modulus if hasattr(encoder, "modulus") else decoder.modulus
+        # device-resident columns: needs the evaluation points (every codec of this module
+        # carries them), a real CUDA context, and a batch worth a kernel launch
+        self._dev = None
+        self._point = getattr(decoder, "point", None) or getattr(encoder, "point", None) or \
+            getattr(robust_decoder, "point", None)
+        if device is True or (device == "auto" and batch_size >= DEVICE_MIN_BATCH):
+            ctx = ntl._ctx(self.modulus)
+            if isinstance(ctx, ntl._native.Context) and self._point is not None:
+                n = self._point.n
+                self._dev = _DeviceColumns(ctx, n, batch_size, degree + 1)
+                self._xs_all = pack_vec(_points(self._point, range(n)), self.modulus)
+            elif device is True:
+                raise ntl._native.NativeLibraryError("device-resident IncrementalDecoder needs the CUDA library")
         self._confirmed_errors = confirmed_errors if confirmed_errors is not None else set()
         self._z = []            # party indices in arrival order
         self._cols = []         # their columns, uint64[batch, 4] each
@@ -325,6 +415,8 @@ class IncrementalDecoder:
 
     def _try_guess(self, idx, col):
         """optimistic path; True while the guess is still standing"""
+        if self._dev is not None:
+            return self._try_guess_device(idx)
         if len(self._z) == self.degree + 1:
             ys = np.stack(self._cols, axis=1)
             self._guess = self.decoder.decode_batch_limbs(self._z, ys)
@@ -337,6 +429,31 @@ class IncrementalDecoder:
         if len(self._z) >= self._need():
             self._result = _GUESS  # the int rows are made on demand (get_results)
             self._result_is_guess = True
+        return True
+
+    def _try_guess_device(self, idx):
+        """The same decision on the device (reed_solomon.py:305-331): decode + re-encode is
+        one kernel when the (degree+1)-th column arrives, every later column costs one compare
+        launch and NO synchronisation; the flags are read once, when enough columns are in for
+        the guess to be accepted.  A mismatch found then sends the decoder down the robust
+        path at the same ``add`` at which the reference's robust path first has enough
+        points (both need ``_min_points_required`` columns), so the observable behaviour
+        -- done(), results, confirmed errors after every add -- is the reference's."""
+        dev = self._dev
+        if len(self._z) == self.degree + 1:
+            xs_k = pack_vec(_points(self._point, self._z), self.modulus)
+            dev.decode_reencode(self._z, xs_k, self._xs_all)
+        else:
+            dev.compare(idx)
+        if len(self._z) < self._need():
+            return True
+        if dev.any_mismatch():
+            logging.critical("Optimistic decoding failed")
+            self._optimistic = False
+            return False
+        self._guess = dev.coefficients()
+        self._result = _GUESS
+        self._result_is_guess = True
         return True
 
     def _robust_rounds(self):
@@ -374,7 +491,9 @@ class IncrementalDecoder:
         col = self._to_column(data)
         self._points_seen.add(idx)
         self._z.append(idx)
-        self._cols.append(col)
+        self._cols.append(col)  # host copy: the (rare) robust path decodes from it
+        if self._dev is not None and self._optimistic:
+            self._dev.put(idx, col)
         if len(self._z) <= self.degree:
             return
         if self._optimistic and self._try_guess(idx, col):

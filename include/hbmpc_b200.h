@@ -184,6 +184,46 @@ int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_ma
                         const uint64_t* ys, size_t batch,
                         uint64_t* coeffs, int32_t* out_len, int32_t* status, int mem);
 
+/* ---- device-resident IncrementalDecoder (reed_solomon.py:232-403) -------------
+ * The reference keeps every received column in Python lists, decodes the first
+ * degree+1 of them (decoder.decode_batch, :311-313), re-encodes the guess
+ * (encoder.encode_batch, :314) and compares each later column with it in a
+ * Python loop (:316-319).  These three entry points keep that inner loop on the
+ * device: columns live in one buffer colbuf[n][batch] (column i = party i's
+ * batch elements, contiguous -- the layout a column arrives in), and only
+ * per-column mismatch flags and the final rows travel back. */
+
+/* rows[b][j] = colbuf[idx[j]][b]  (j < k): the (batch x k) matrix of the k chosen
+ * columns, row-major, as the interpolation kernels read it.  Device pointers. */
+int hbg_columns_to_rows(hbg_ctx* ctx, const uint64_t* colbuf, size_t batch,
+                        const int32_t* idx, int k, uint64_t* rows);
+
+/* Fused decode -> re-encode (reed_solomon.py:311-314): for every row the k
+ * coefficients of the polynomial through (xs_k[i], ys[b][i]) AND its n evaluations
+ * at xs_all, from ONE constant matrix [V(xs_k)^-1 ; V(xs_all) V(xs_k)^-1]:
+ *   out[b][0..k)   = coefficients,   out[b][k..k+n) = evaluations.
+ * HBG_ERR_SINGULAR if the xs_k repeat. */
+int hbg_interpolate_reencode(hbg_ctx* ctx, const uint64_t* xs_k, int k,
+                             const uint64_t* xs_all, int n,
+                             const uint64_t* ys, size_t batch,
+                             uint64_t* out, int mem);
+
+/* Column validation (reed_solomon.py:316-319) for m columns at once:
+ *   flags[j] = 1 if colbuf[idx[j]][b] != rows[b][col_offset + idx[j]] for some b,
+ *   else 0   (rows has row_width elements per row; for the output of
+ *   hbg_interpolate_reencode: row_width = k+n, col_offset = k).
+ * rows / colbuf are device pointers; flags_dev is a device int32[m] (always
+ * written); if flags_host is non-NULL the flags are also copied there and the
+ * call returns after they have arrived. */
+int hbg_compare_columns(hbg_ctx* ctx, const uint64_t* rows, int row_width, int col_offset,
+                        const uint64_t* colbuf, size_t batch,
+                        const int32_t* idx, int m,
+                        int32_t* flags_dev, int32_t* flags_host);
+
+/* Test hook: bound (bytes) of the per-context cache of device constants; when it
+ * is exceeded the cache is dropped at the entry of the next call (default 256 MB). */
+int hbg_ctx_set_cache_limit(hbg_ctx* ctx, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

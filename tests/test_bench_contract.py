@@ -38,6 +38,17 @@ def test_reference_arm_line():
                         "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_ignores_torchrun_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must still use every core of the box
+    (round 1's N >= 2 reference lines ran on one thread and inflated the ratio ~16x)"""
+    res = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--batch", "4096"],
+              env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1"})
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["batch_polys_per_step"] == 4096
+
+
 def test_reference_arm_other_ranks_are_silent():
     res = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
               env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})

@@ -90,18 +90,26 @@ def test_vandermonde_vs_oracle(ntl, p, n, d, batch):
     polys = [[rng.randrange(p) for _ in range(rng.randint(1, d))] for _ in range(batch)]
     polys[0] = polys[0] + [p - 1] * (d - len(polys[0]))
     want = orc.vandermonde_batch_evaluate(xs, polys, p)
-    for path in ("auto", "global", "smem", "small", "small-r29"):
+    paths = ("auto", "global", "smem", "small", "small-r29", "no-tc") + (("tc",) if p == P else ())
+    for path in paths:
         ntl._ctx(p).set_matvec_path(path)
         assert ntl.vandermonde_batch_evaluate(xs, polys, p) == want, path
+        if path == "tc" and n * d <= 96:
+            assert ntl._ctx(p).last_kernel() == "tc_apply_kernel"
     if p > n:
         k = d
         xk = rng.sample(xs, k)
         ys = [[rng.randrange(p) for _ in range(k)] for _ in range(batch)]
         want = orc.vandermonde_batch_interpolate(xk, ys, p)
-        for path in ("auto", "global", "smem", "small", "small-r29"):
+        for path in paths:
             ntl._ctx(p).set_matvec_path(path)
             assert ntl.vandermonde_batch_interpolate(xk, ys, p) == want, path
+            if path == "tc" and k * k <= 96:
+                assert ntl._ctx(p).last_kernel() == "tc_apply_kernel"
     ntl._ctx(p).set_matvec_path("auto")
+    if p != P:
+        with pytest.raises(NotImplementedError):  # the tensor-core path is BLS12-381 only
+            ntl._ctx(p).set_matvec_path("tc")
 
 
 def test_worst_case_values(ntl):
@@ -132,6 +140,55 @@ def test_fft_vs_oracle(ntl, r, d, k, batch):
         assert ntl.fft_batch_evaluate(polys, omega, P, n, k) == want, path
     ntl._ctx(P).set_fft_path("auto")
     assert ntl.fft_batch_evaluate(polys, omega, P, n, k) == want
+    ntl._ctx(P).set_matvec_path("tc")  # the matrix form on the tensor cores, where it fits
+    assert ntl.fft_batch_evaluate(polys, omega, P, n, k) == want
+    ntl._ctx(P).set_matvec_path("auto")
+
+
+def test_tensor_core_path(ntl):
+    """tc_apply_kernel (exact u8 GEMM on tcgen05 + Barrett epilogue) against the oracle and
+    against the IMAD kernels: tile-boundary batch sizes, extreme operands, every block shape
+    (outputs per accumulator block 1..8, one and several blocks)."""
+    ctx = ntl._ctx(P)
+    rng = random.Random(0x7C)
+    shapes = [(1, 1), (2, 2), (3, 2), (4, 4), (5, 3), (6, 6), (7, 5), (8, 8), (16, 6), (12, 7), (9, 2),
+              (24, 4), (6, 10), (2, 16), (32, 3)]
+    try:
+        for n, d in shapes:
+            xs = rng.sample(range(1, 1 << 20), n)
+            for batch in (1, 127, 128, 129, 300, 1500):
+                polys = [[rng.randrange(P) for _ in range(d)] for _ in range(batch)]
+                polys[0] = [P - 1] * d
+                polys[-1] = [0] * d
+                if batch > 2:
+                    polys[1] = [(P - 1) if j % 2 else 1 for j in range(d)]
+                ctx.set_matvec_path("tc")
+                got = ntl.vandermonde_batch_evaluate(xs, polys, P)
+                assert ctx.last_kernel() == "tc_apply_kernel", (n, d)
+                ctx.set_matvec_path("no-tc")
+                assert got == ntl.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch)
+                assert ctx.last_kernel() != "tc_apply_kernel"
+                if batch <= 129:
+                    assert got == orc.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch)
+        # auto mode: large batches take the tensor-core kernel, small ones the IMAD kernels
+        ctx.set_matvec_path("auto")
+        xs = list(range(1, 7))
+        ys = [[rng.randrange(P) for _ in range(6)] for _ in range(600)]
+        a = ntl.vandermonde_batch_interpolate(xs, ys, P)
+        assert ctx.last_kernel() == "tc_apply_kernel"
+        b = ntl.vandermonde_batch_interpolate(xs, ys[:100], P)
+        assert ctx.last_kernel() != "tc_apply_kernel" and a[:100] == b
+        assert a[:40] == orc.vandermonde_batch_interpolate(xs, ys[:40], P)
+        # non-canonical limbs (>= p, up to 2^256 - 1) reduce like to_ZZ_p would
+        raw = np.full((256, 6, 4), 2 ** 64 - 1, dtype=np.uint64)
+        raw[::2, :, 3] = np.uint64(P >> 192)
+        xl = ntl.pack_vec(xs, P)
+        ctx.set_matvec_path("tc")
+        got = ntl.unpack_rows(ntl.vandermonde_batch_interpolate_limbs(xl, raw, P))
+        want = orc.vandermonde_batch_interpolate(xs, [[v % P for v in row] for row in ntl.unpack_rows(raw)], P)
+        assert got == want
+    finally:
+        ctx.set_matvec_path("auto")
 
 
 def test_fft_small_prime(ntl):
@@ -239,7 +296,7 @@ def test_config5_shard_round_trip(ntl):
     enc = ntl.fft_batch_evaluate_limbs(c, omega, P, pt.order, n)
     zs = sorted(random.Random(5).sample(range(n), k))
     ys = np.ascontiguousarray(enc[:, zs, :])
-    for path in ("auto", "global", "smem", "small-r29"):
+    for path in ("auto", "global", "smem", "small-r29", "tc"):
         ntl._ctx(P).set_matvec_path(path)
         assert np.array_equal(ntl.fft_batch_interpolate_limbs(zs, ys, omega, P, pt.order), c), path
     ntl._ctx(P).set_matvec_path("auto")

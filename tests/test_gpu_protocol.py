@@ -206,6 +206,65 @@ def test_incremental_decoder_differential(rs):
         logging.disable(logging.NOTSET)
 
 
+def test_incremental_decoder_device_resident(rs, monkeypatch):
+    """The device-resident column path (hbg_columns_to_rows / hbg_interpolate_reencode /
+    hbg_compare_columns) must be indistinguishable from the host path and from the reference:
+    (a) the differential schedules again with every decoder forced onto the device path,
+    (b) a batch large enough for the tensor-core kernel, honest and with one lying party."""
+    import json
+    import logging
+    import os
+    import sys
+
+    import differential as d
+    import numpy as np
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_incremental_golden as mig
+
+    with open(os.path.join(here, "golden", "incremental_traces_v1.json")) as fh:
+        gold = json.load(fh)
+    monkeypatch.setattr(rs, "DEVICE_MIN_BATCH", 1)
+    before = rs._DeviceColumns.totals["decoders"]
+    logging.disable(logging.CRITICAL)
+    try:
+        for seed in range(0, 400):
+            s = d.verdict_fixture() if seed == 0 else d.make_schedule(seed)
+            ours = d.run_trace(d.ours_decoder(s), s)
+            dig, length, _ = gold["traces"][seed]
+            assert (mig.digest(ours), len(ours)) == (dig, length), f"schedule {seed} on the device path"
+        assert rs._DeviceColumns.totals["decoders"] - before == 400
+
+        n, t, batch = 16, 5, 3000
+        rng = random.Random(77)
+        for omega in (False, True):
+            pt = _point(n, omega)
+            polys = [[rng.randrange(P) for _ in range(t + 1)] for _ in range(batch)]
+            cols = np.ascontiguousarray(
+                rs.EncoderFactory.get(pt).encode_batch_limbs(rs.pack_rows(polys, t + 1, P)).transpose(1, 0, 2))
+            lie = cols[7].copy()
+            lie[batch - 1, 0] ^= np.uint64(1)  # one element of one row
+            for bad in (None, 7):
+                traces = []
+                for device in (True, False):
+                    inc = rs.IncrementalDecoder(rs.EncoderFactory.get(pt), rs.DecoderFactory.get(pt),
+                                                rs.RobustDecoderFactory.get(t, pt), t, batch, t, device=device)
+                    tr = []
+                    for i in [3, 9, 0, 7, 12, 15, 1, 2, 4, 5, 6, 8, 10]:
+                        inc.add(i, (lie if i == bad else cols[i]).tobytes())
+                        tr.append((inc.done(), sorted(inc.get_results()[1] or [])))
+                        if inc.done():
+                            break
+                    res, errs = inc.get_results_limbs()
+                    assert np.array_equal(res, rs.pack_rows(polys, t + 1, P)) and errs == ({bad} if bad else set())
+                    traces.append(tr)
+                assert traces[0] == traces[1]
+                assert len(traces[0]) == (11 if bad is None else 12)
+    finally:
+        logging.disable(logging.NOTSET)
+
+
 # --- batch_reconstruct (tests/test_batch_reconstruction.py:12-170) -------------
 
 

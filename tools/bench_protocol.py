@@ -24,15 +24,36 @@ async def once(wire):
     jobs = [batch_reconstruct(shares[i], P, t, n, i, net.sends[i], net.recvs[i], wire=wire) for i in range(n)]
     return await asyncio.gather(*jobs)
 
-for wire in ("ints", "limbs"):
-    loop = asyncio.new_event_loop()
-    res = loop.run_until_complete(once(wire))
-    assert [e.value for e in res[0]] == secrets
-    t0 = time.perf_counter()
-    loop.run_until_complete(once(wire))
-    dt = time.perf_counter() - t0
-    print(f"wire={wire}: B={B} shares, n={n}: {dt:.3f} s for all {n} parties = {dt/n*1e3:.1f} ms per party, {B/(dt/n):.3e} shares/s per party")
-    if wire == "limbs" and len(sys.argv) > 2:
-        pr = cProfile.Profile(); pr.enable(); loop.run_until_complete(once(wire)); pr.disable()
-        pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
-    loop.close()
+import json
+from honeybadgermpc_b200 import reed_solomon as rs
+
+out_lines = []
+for mode in ("device", "host"):
+    # "host": round 1's IncrementalDecoder (columns as host limb arrays, every decode / encode a
+    # HBG_MEM_HOST round trip, numpy compare); "device": columns resident in HBM, fused
+    # decode+re-encode kernel, compare kernel, flags + final rows come back
+    rs.DEVICE_MIN_BATCH = 256 if mode == "device" else 1 << 60
+    for wire in ("ints", "limbs"):
+        loop = asyncio.new_event_loop()
+        res = loop.run_until_complete(once(wire))
+        assert [e.value for e in res[0]] == secrets
+        for key in rs._DeviceColumns.totals:
+            rs._DeviceColumns.totals[key] = 0
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            loop.run_until_complete(once(wire))
+        dt = (time.perf_counter() - t0) / reps
+        tot = dict(rs._DeviceColumns.totals)
+        per = {k: v / max(1, tot["decoders"]) for k, v in tot.items() if k != "decoders"}
+        line = {"tool": "bench_protocol", "incremental_decoder": mode, "wire": wire, "n": n, "t": t,
+                "shares_per_open": B, "ms_per_party_per_open": dt / n * 1e3,
+                "shares_per_s_per_party": B / (dt / n),
+                "per_decoder": per if mode == "device" else None,
+                "decoders_per_open_per_party": 2}
+        out_lines.append(line)
+        print(json.dumps(line), flush=True)
+        if wire == "limbs" and len(sys.argv) > 2:
+            pr = cProfile.Profile(); pr.enable(); loop.run_until_complete(once(wire)); pr.disable()
+            pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+        loop.close()
