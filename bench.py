@@ -173,6 +173,122 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg5(args, world, rank, local, dev):
+    """BASELINE configs[4] as a STRONG-scaling record: n = 128, t = 42; 1 048 576 polynomials in
+    total, the batch axis sharded over the ranks; one pass = NTT-128 encode of this rank's shard
+    + interpolation from 43 scattered shares + all-gather, so that every rank ends up with all
+    2^20 x 43 opened values.  The shard is processed in pieces so the gather of one piece
+    overlaps the kernels of the next.  Returns the dict stored under "cfg5_strong"."""
+    import random
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from honeybadgermpc_b200 import _native
+    from honeybadgermpc_b200.field import GF
+    from honeybadgermpc_b200.ntl import pack_vec
+    from honeybadgermpc_b200.polynomial import EvalPoint
+    from honeybadgermpc_b200.sharding import ShardedReconstructor
+
+    n, k = 128, 43
+    total = args.cfg5_polys
+    shard = total // world
+    piece = min(shard, args.cfg5_piece)
+    parts = shard // piece
+    pt = EvalPoint(GF(P), n, True)
+    omega = pack_vec([pt.omega.value], P)[0]
+    zs = sorted(random.Random(5).sample(range(n), k))
+    gather = "auto" if args.gather == "fused" else args.gather  # k = 43: no fused epilogue
+    rec = ShardedReconstructor(P, omega, pt.order, zs, piece, device=local, depth=2, gather=gather,
+                               copy_ctas=args.gather_ctas, parts=parts)
+    ctx, stream = rec.ctx, rec.stream
+    enc_stream = torch.cuda.Stream(device=dev)
+    ctx_enc = _native.Context(P, device=local)
+    ctx_enc.set_stream(enc_stream.cuda_stream)
+    rng = np.random.default_rng(0xB205 + rank)
+    zs_t = torch.tensor(zs, device=dev)
+    with torch.cuda.stream(stream):
+        c = torch.from_numpy(rng.integers(0, 2 ** 62, size=(shard, k, 4), dtype=np.uint64).view(np.int64)).to(dev)
+        e = torch.empty((shard, n, 4), dtype=torch.int64, device=dev)
+        ctx.fft_batch_evaluate(omega, pt.order, c.data_ptr(), shard, k, n, e.data_ptr(), _native.MEM_DEVICE)
+        y = e.index_select(1, zs_t).contiguous()
+        e.zero_()
+    stream.synchronize()
+    names = {"encode": ctx.last_kernel()}
+    pb_c, pb_e, pb_y = piece * k * E, piece * n * E, piece * k * E
+
+    def one_pass(slot):
+        enc_stream.wait_stream(stream)
+        for p in range(parts):
+            ctx_enc.fft_batch_evaluate(omega, pt.order, c.data_ptr() + p * pb_c, piece, k, n,
+                                       e.data_ptr() + p * pb_e, _native.MEM_DEVICE)
+            rec.open(y.data_ptr() + p * pb_y, slot=slot, part=p)
+        stream.wait_stream(enc_stream)
+        rec.finish(slot)
+        if rec.handles or rec.world == 1:
+            stream.wait_event(rec.done_ev[slot])  # the pass ends when every rank's pieces have landed
+        else:
+            with torch.cuda.stream(stream):
+                rec.wait(slot)
+
+    def barrier():
+        rec.drain()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(2):
+        one_pass(w % 2)
+    names["interpolate"] = ctx.last_kernel()
+    barrier()
+    passes = args.cfg5_passes
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(passes):
+        one_pass(i % 2)
+    t1.record(stream)
+    barrier()
+    ms = t0.elapsed_time(t1) / passes
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    g = rec.gathered[(passes - 1) % 2]
+    assert torch.equal(g[rank * shard:(rank + 1) * shard], c), "cfg5: decoded shard != coefficients"
+    assert torch.equal(e.index_select(1, zs_t), y), "cfg5: encode output is wrong"
+    if world > 1:
+        sums = g.view(world, -1).sum(dim=1)
+        lo, hi = sums.clone(), sums.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "cfg5: ranks disagree on the gathered result"
+    # per-kernel time of one piece (serial, events)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ctx_enc.set_stream(stream.cuda_stream)
+    ev[0].record(stream)
+    ctx_enc.fft_batch_evaluate(omega, pt.order, c.data_ptr(), piece, k, n, e.data_ptr(), _native.MEM_DEVICE)
+    ev[1].record(stream)
+    ctx.fft_batch_interpolate(omega, pt.order, np.ascontiguousarray(zs, dtype=np.int32), y.data_ptr(), piece,
+                              rec.own_block_ptr(0, 0), _native.MEM_DEVICE)
+    ev[2].record(stream)
+    barrier()
+    ingress = (world - 1) * shard * k * E
+    out = {"workload": "n=128 t=42 NTT-128 encode + interpolate from 43 scattered shares + all-gather "
+                       "(BASELINE configs[4]), STRONG scaling: the total is fixed",
+           "total_polys": total, "polys_per_gpu": shard, "piece": piece, "scaling": "strong",
+           "ms_per_pass": ms, "value": total * k / (ms * 1e-3), "unit": UNIT, "passes": passes,
+           "gather": rec.mode, "kernels": names,
+           "kernel_ms_per_piece": {"encode": ev[0].elapsed_time(ev[1]), "interpolate": ev[1].elapsed_time(ev[2])},
+           "nvlink_ingress_bytes_per_pass": ingress,
+           "nvlink_floor_ms": ingress / 770e9 * 1e3,
+           "algorithmic_GBps": total / world * (3 * k + n) * E / (ms * 1e-3) / 1e9}
+    del rec, c, e, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -257,6 +373,7 @@ def run_b200(args):
         rec.open(y_ptr[s], slot=i % depth)
         if evs is not None:
             evs[2].record(stream)
+        rec.finish(i % depth)  # no reader in the benchmark: the slot is handed back at once
 
     def barrier():
         rec.drain()
@@ -290,7 +407,7 @@ def run_b200(args):
                 print(f"[bench] CUDA graph capture failed ({exc!r}); eager step loop", file=sys.stderr)
             graph = None
             barrier()
-    launches_per_step = 2 + (1 if rec.mode.endswith("copy") else 0)
+    launches_per_step = 2 + (3 if rec.signal else 1 if rec.mode.endswith("copy") else 0)
 
     def run_steps(n_steps):
         """enqueue n_steps (a multiple of `unit` when the graph is used)"""
@@ -472,6 +589,15 @@ def run_b200(args):
            "boundary": "hbg_fft_batch_evaluate + hbg_fft_batch_interpolate, HBG_MEM_HOST, pinned buffers, "
                        "host_async on, hbg_ctx_synchronize at the end of every step"}
 
+    cfg5 = None
+    if args.cfg5 == "on" or (args.cfg5 == "auto" and args.batch == 65536):
+        try:
+            cfg5 = run_cfg5(args, world, rank, local, dev)
+        except Exception as exc:  # noqa: BLE001 - the headline line must still be printed
+            cfg5 = {"error": repr(exc)}
+            if world > 1:
+                raise
+
     line = None
     if rank == 0:
         cpu = None
@@ -501,7 +627,7 @@ def run_b200(args):
                                      else "eager Python loop"),
                        "parallelism": f"batch shard x{world}" + (f" + all-gather ({rec.mode})" if world > 1 else ""),
                        "polys_per_s": value / K},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "cfg5_strong": cfg5,
             "gpu_launches": launches_per_step * steps,
             "host_enqueue_ms_per_step": (host_enqueued - host_t0) * 1e3 / steps,
             "clocks": sampler.result(host_t0, host_t1),
@@ -528,12 +654,18 @@ def main():
                     help="with overlapped streams: record per-kernel events on every n-th step only")
     ap.add_argument("--serial", action="store_true",
                     help="N=1: run the two kernels of a step back to back on one stream")
-    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "copy", "nccl"],
-                    help="N>1: auto = the interpolation kernel stores its block into every rank's "
-                         "symmetric-memory buffer itself (multimem.st when a multicast address exists); "
-                         "p2p = the same with peer stores only; copy = separate side-stream copy kernel; "
-                         "nccl = overlapped NCCL all-gather")
-    ap.add_argument("--gather-ctas", type=int, default=16)
+    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "mc", "p2p", "fused", "copy", "nccl"],
+                    help="N>1: auto = ce = local store + copy-engine peer copies on a side stream, slot hand-over "
+                         "by device flags; mc = multimem.st copy kernel + flags; p2p = peer-store copy kernel "
+                         "+ flags; "
+                         "fused = the kernel epilogue stores into every rank's buffer, two symmetric-memory "
+                         "barriers per step; copy = copy kernel + barriers; nccl = overlapped NCCL all-gather")
+    ap.add_argument("--gather-ctas", type=int, default=64)
+    ap.add_argument("--cfg5", default="auto", choices=["auto", "on", "off"],
+                    help="also run BASELINE configs[4] (n=128, 2^20 polynomials in total) as a strong-scaling record")
+    ap.add_argument("--cfg5-polys", type=int, default=1 << 20)
+    ap.add_argument("--cfg5-piece", type=int, default=16384)
+    ap.add_argument("--cfg5-passes", type=int, default=5)
     ap.add_argument("--min-ms", type=float, default=60.0,
                     help="the timed region is extended (more steps) until it lasts at least this long")
     ap.add_argument("--no-graph", action="store_true", help="eager Python step loop instead of a CUDA graph")

@@ -92,6 +92,23 @@ SIGNATURES = {
          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
          ctypes.c_int]),
     "hbg_ctx_set_cache_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "hbg_ctx_set_interp_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "hbg_allgather_block_signal": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hbg_allgather_block_ce": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+         ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hbg_gather_wait": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+         ctypes.c_int]),
+    "hbg_gather_release": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hbg_columns_to_rows": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -268,6 +285,28 @@ class Context:
         self._check(self.lib.hbg_compare_columns(
             self.handle, int(rows_ptr), row_width, col_offset, int(colbuf_ptr), batch, _ptr(idx), len(idx),
             int(flags_dev_ptr), _ptr(flags_host)))
+
+    def set_interp_path(self, path):
+        self._check(self.lib.hbg_ctx_set_interp_path(self.handle, {"auto": 0, "matrix": 1, "fnt": 2}[path]))
+
+    def allgather_block_signal(self, block_ptr, nbytes, peer_arr, multicast_ptr, offset_bytes, rank,
+                               max_ctas, flags_arr, n_slots, slot, parts, first_part):
+        self._check(self.lib.hbg_allgather_block_signal(
+            self.handle, int(block_ptr), nbytes, peer_arr, int(multicast_ptr) if multicast_ptr else None,
+            offset_bytes, len(peer_arr), rank, max_ctas, flags_arr, n_slots, slot, parts,
+            1 if first_part else 0))
+
+    def allgather_block_ce(self, block_ptr, nbytes, peer_arr, offset_bytes, rank, flags_arr, n_slots, slot,
+                           parts, first_part):
+        self._check(self.lib.hbg_allgather_block_ce(
+            self.handle, int(block_ptr), nbytes, peer_arr, offset_bytes, len(peer_arr), rank, flags_arr,
+            n_slots, slot, parts, 1 if first_part else 0))
+
+    def gather_wait(self, flags_arr, rank, n_slots, slot, parts):
+        self._check(self.lib.hbg_gather_wait(self.handle, flags_arr, len(flags_arr), rank, n_slots, slot, parts))
+
+    def gather_release(self, flags_arr, rank, n_slots, slot):
+        self._check(self.lib.hbg_gather_release(self.handle, flags_arr, len(flags_arr), rank, n_slots, slot))
 
     def gao_decode_batch(self, xs, k, ys, batch, coeffs, locator, loc_stride, loc_len, status,
                          mem=MEM_HOST):

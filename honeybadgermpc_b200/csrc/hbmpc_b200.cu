@@ -53,11 +53,13 @@ struct hbg_ctx {
                         // 5 tensor-core kernel (tc_kernels.cuh), 6 never the tensor-core kernel
   unsigned tc_mu = 0;   // floor(2^280 / p) when the tensor-core path serves this modulus, else 0
   unsigned* tc_error = nullptr;  // device word set by a barrier watchdog of tc_apply_kernel
+  unsigned* gather_counter = nullptr;  // last-CTA detection of gather_copy_signal_kernel
   int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
+  int interp_path = 0;  // fft_batch_interpolate: 0 auto, 1 V^-1 matrix, 2 NTT-structured (fnt_decode_step2)
   std::string err;
   uint64_t launches = 0;
   const char* last_kernel = "";
-  DevBuf in, out, work, work2;
+  DevBuf in, out, work, work2, fnt_a, fnt_b;
   // host-buffer pipeline: H2D / D2H streams and a ring of staging slots, so that with
   // hbg_ctx_set_host_async consecutive calls overlap (call i+1's H2D under call i's D2H)
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -734,6 +736,201 @@ int interp_matrix(hbg_ctx* ctx, const std::string& key, int k, const void** d_m,
 
 
 // ---------------------------------------------------------------------------
+// NTT-structured interpolation (fnt_decode_step1/2, rsdecode_impl.h:194-265).
+//   step 1 (host, once per (omega, n, zs), O(k^2)): A = prod (X - x_i), d_i = 1 / A'(x_i),
+//           and the transform of A for the truncated product of step 2;
+//   step 2 (device, per row): N = sum_i (y_i d_i) X^{z_i}; R = first k+1 values of the size-n
+//           transform of N with omega^-1; Q_j = -R_{(j+1) mod n}; P = Q * A mod X^k -- the
+//           product as a cyclic convolution of size m >= 2k (forward NTT, pointwise
+//           multiply with the cached transform of A scaled by 1/m, inverse NTT).
+// No V^-1 (O(k^3) on the host) is ever formed on this path.
+// ---------------------------------------------------------------------------
+struct FntConst {
+  const void* d_scale = nullptr;   // [k] 1/A'(x_i), Montgomery
+  const void* d_zs = nullptr;      // [k] int
+  const void* d_ahat = nullptr;    // [m] NTT_m(A) / m, Montgomery
+  uint64_t omega_inv[4], wm[4], wm_inv[4];
+  int m = 0;
+};
+
+// a primitive m-th root of unity (m a power of two) in Montgomery form, or false
+bool find_root(const HostField& f, const FieldParams& fp, int m, Fe* root) {
+  // (p - 1) / m must be exact
+  uint32_t pm1[8];
+  memcpy(pm1, fp.p, 32);
+  pm1[0] -= 1;  // p is odd
+  if (m > 1) {
+    int bits = 0;
+    while ((1 << bits) < m) bits++;
+    for (int b = 0; b < bits; b++)
+      if ((pm1[b / 32] >> (b % 32)) & 1u) return false;
+    for (int b = 0; b < bits; b++) {  // pm1 >>= 1
+      for (int w = 0; w < 8; w++) pm1[w] = (pm1[w] >> 1) | (w < 7 ? pm1[w + 1] << 31 : 0);
+    }
+  }
+  Fe e;
+  memcpy(e.w, pm1, 32);
+  const Fe minus_one = f.neg(f.one());
+  for (uint32_t x = 2; x < 200; x++) {
+    Fe y = f.pow(f.from_small(x), e);
+    if (m == 1) {
+      *root = f.one();
+      return true;
+    }
+    if (fe_eq(f.pow_u64(y, (uint64_t)m / 2), minus_one)) {
+      *root = y;
+      return true;
+    }
+  }
+  return false;
+}
+
+void fe_to_std_u64(const HostField& f, const Fe& mont, uint64_t out[4]) {
+  Fe s = f.from_mont(mont);
+  fe_to_u64(s, out);
+}
+
+// host step 1; HBG_ERR_UNSUPPORTED when the field has no root of unity of the order the
+// convolution needs (the caller then uses the matrix path)
+int fnt_constants(hbg_ctx* ctx, const uint64_t omega[4], int n, const int32_t* zs, int k, FntConst* fc) {
+  const HostField& f = *ctx->field;
+  int m = 1;
+  while (m < 2 * k) m <<= 1;
+  fc->m = m;
+  Fe w;
+  int rc = check_omega(ctx, omega, n, w);
+  if (rc) return rc;
+  for (int i = 0; i < k; i++)
+    if (zs[i] < 0 || zs[i] >= n) return fail(ctx, HBG_ERR_INVALID, "z outside [0, n)");
+  Fe wm;
+  if (!find_root(f, ctx->fp, m, &wm))
+    return fail(ctx, HBG_ERR_UNSUPPORTED, "no root of unity of the order the truncated product needs");
+  fe_to_std_u64(f, f.inv(w), fc->omega_inv);
+  fe_to_std_u64(f, wm, fc->wm);
+  fe_to_std_u64(f, f.inv(wm), fc->wm_inv);
+  const std::string key = make_key("fnt", omega, 32, zs, (size_t)k * 4, n, k);
+  rc = get_const(ctx, key + "|s", &fc->d_scale, [&](std::vector<uint32_t>& host) {
+    std::vector<Fe> xs(k);
+    for (int i = 0; i < k; i++) xs[i] = f.pow_u64(w, (uint64_t)zs[i]);
+    std::vector<Fe> a = build_from_roots(f, xs);  // k + 1 coefficients
+    std::vector<Fe> ad(k);                        // derivative
+    for (int i = 0; i < k; i++) ad[i] = f.mul(f.from_small((uint32_t)(i + 1)), a[i + 1]);
+    std::vector<Fe> ev(k);
+    for (int i = 0; i < k; i++) ev[i] = horner(f, ad, xs[i]);
+    if (!f.batch_inv(ev)) return fail(ctx, HBG_ERR_SINGULAR, "repeated z");
+    host.resize((size_t)k * 8);
+    for (int i = 0; i < k; i++) memcpy(&host[(size_t)i * 8], ev[i].w, 32);
+    // the transform of A, scaled by 1/m, goes to a second cache entry
+    std::vector<Fe> ah((size_t)m, fe_zero());
+    for (int i = 0; i <= k; i++) ah[i] = a[i];
+    host_ntt(f, ah, wm);
+    const Fe minv = f.inv(f.from_small((uint32_t)m));
+    std::vector<uint32_t> h2((size_t)m * 8);
+    for (int i = 0; i < m; i++) {
+      const Fe v = f.mul(ah[i], minv);
+      memcpy(&h2[(size_t)i * 8], v.w, 32);
+    }
+    ctx->host_cache[key + "|a"] = h2;
+    return HBG_OK;
+  });
+  if (rc) return rc;
+  rc = get_const(ctx, key + "|a", &fc->d_ahat, [&](std::vector<uint32_t>& host) {
+    auto it = ctx->host_cache.find(key + "|a");
+    if (it == ctx->host_cache.end()) return fail(ctx, HBG_ERR_CUDA, "fnt constants out of sync");
+    host = it->second;
+    ctx->host_cache.erase(it);
+    return HBG_OK;
+  });
+  if (rc) return rc;
+  return get_const(ctx, key + "|z", &fc->d_zs, [&](std::vector<uint32_t>& host) {
+    host.resize((size_t)k);
+    for (int i = 0; i < k; i++) host[i] = (uint32_t)zs[i];
+    return HBG_OK;
+  });
+}
+
+template <class K>
+int launch_fnt_kernel(hbg_ctx* ctx, K kernel, const FntArgs& a, unsigned long long elems) {
+  unsigned long long blocks = (elems + 255) / 256;
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return HBG_OK;
+  kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return HBG_OK;
+}
+
+int launch_ntt(hbg_ctx* ctx, const void* d_tw, const std::vector<uint32_t>* h_tw, int n, const void* d_in,
+               int d, void* d_out, int k_out, size_t batch);
+
+int fnt_interpolate(hbg_ctx* ctx, const FntConst& fc, int n, int k, const void* d_ys, size_t batch,
+                    void* d_out) {
+  const int m = fc.m, kr = k + 1 < n ? k + 1 : n;
+  const void *tw_n = nullptr, *tw_m = nullptr, *tw_mi = nullptr;
+  const std::vector<uint32_t>*h_n = nullptr, *h_m = nullptr, *h_mi = nullptr;
+  int rc = twiddles(ctx, fc.omega_inv, n, &tw_n, &h_n);
+  if (rc) return rc;
+  rc = twiddles(ctx, fc.wm, m, &tw_m, &h_m);
+  if (rc) return rc;
+  rc = twiddles(ctx, fc.wm_inv, m, &tw_mi, &h_mi);
+  if (rc) return rc;
+  rc = bind_field(ctx);
+  if (rc) return rc;
+  const size_t wide = (size_t)(n > m ? n : m);
+  size_t chunk = ((size_t)1 << 30) / (wide * 32);
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  rc = ensure(ctx, ctx->fnt_a, chunk * wide * 32);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->fnt_b, chunk * (size_t)(kr + k) * 32);
+  if (rc) return rc;
+  uint4* buf_a = (uint4*)ctx->fnt_a.p;
+  uint4* buf_r = (uint4*)ctx->fnt_b.p;
+  uint4* buf_q = buf_r + 2 * chunk * (size_t)kr;
+  for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+    const size_t rows = batch - r0 < chunk ? batch - r0 : chunk;
+    FntArgs a;
+    memset(&a, 0, sizeof a);
+    a.batch = rows;
+    a.k = k;
+    a.n = n;
+    a.m = m;
+    // N = scatter of y_i / A'(x_i)
+    CU(cudaMemsetAsync(buf_a, 0, rows * (size_t)n * 32, ctx->stream));
+    a.in = (const uint4*)d_ys + 2 * r0 * (size_t)k;
+    a.out = buf_a;
+    a.cst = (const uint4*)fc.d_scale;
+    a.zs = (const int*)fc.d_zs;
+    rc = ctx->is_bls ? launch_fnt_kernel(ctx, fnt_scale_scatter_kernel<FieldBLS>, a, rows * (size_t)k)
+                     : launch_fnt_kernel(ctx, fnt_scale_scatter_kernel<FieldAny>, a, rows * (size_t)k);
+    if (rc) return rc;
+    // R = first kr values of the transform with omega^-1
+    rc = launch_ntt(ctx, tw_n, h_n, n, buf_a, n, buf_r, kr, rows);
+    if (rc) return rc;
+    // Q_j = -R_{(j+1) mod n}
+    a.in = buf_r;
+    a.out = buf_q;
+    rc = ctx->is_bls ? launch_fnt_kernel(ctx, fnt_shift_negate_kernel<FieldBLS>, a, rows * (size_t)k)
+                     : launch_fnt_kernel(ctx, fnt_shift_negate_kernel<FieldAny>, a, rows * (size_t)k);
+    if (rc) return rc;
+    // P = Q * A mod X^k through a size-m cyclic convolution
+    rc = launch_ntt(ctx, tw_m, h_m, m, buf_q, k, buf_a, m, rows);
+    if (rc) return rc;
+    a.in = buf_a;
+    a.out = buf_a;
+    a.cst = (const uint4*)fc.d_ahat;
+    rc = ctx->is_bls ? launch_fnt_kernel(ctx, fnt_pointwise_kernel<FieldBLS>, a, rows * (size_t)m)
+                     : launch_fnt_kernel(ctx, fnt_pointwise_kernel<FieldAny>, a, rows * (size_t)m);
+    if (rc) return rc;
+    rc = launch_ntt(ctx, tw_mi, h_mi, m, buf_a, m, (uint4*)d_out + 2 * r0 * (size_t)k, k, rows);
+    if (rc) return rc;
+  }
+  ctx->last_kernel = "fnt_decode_step2";
+  return HBG_OK;
+}
+
+// ---------------------------------------------------------------------------
 // robust decoders
 // ---------------------------------------------------------------------------
 size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -988,6 +1185,11 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
   }
   ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // device words of the gather hand-over kernels (allocated here: the calls that use them
+  // must be capturable into CUDA graphs, so they may not allocate)
+  if (cudaMalloc(&ctx->gather_counter, 2 * sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(ctx->gather_counter, 0, 2 * sizeof(unsigned)) != cudaSuccess)
+    ctx->gather_counter = nullptr;
   if (ctx->is_bls) {  // the tensor-core path is instantiated for the BLS12-381 scalar field
     ctx->tc_mu = barrett_mu280(fp);
     if (cudaMalloc(&ctx->tc_error, sizeof(unsigned)) != cudaSuccess ||
@@ -1010,7 +1212,10 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->work.p) cudaFree(ctx->work.p);
   if (ctx->work2.p) cudaFree(ctx->work2.p);
   if (ctx->tc_error) cudaFree(ctx->tc_error);
+  if (ctx->gather_counter) cudaFree(ctx->gather_counter);
   if (ctx->flags.p) cudaFree(ctx->flags.p);
+  if (ctx->fnt_a.p) cudaFree(ctx->fnt_a.p);
+  if (ctx->fnt_b.p) cudaFree(ctx->fnt_b.p);
   if (ctx->s_in) {
     cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->s_out);
@@ -1067,6 +1272,12 @@ int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
   if (!ctx || path < 0 || path > 6) return HBG_ERR_INVALID;
   if (path == 5 && !ctx->tc_mu) return fail(ctx, HBG_ERR_UNSUPPORTED, "the tensor-core path serves the BLS12-381 scalar field only");
   ctx->matvec_path = path;
+  return HBG_OK;
+}
+
+int hbg_ctx_set_interp_path(hbg_ctx* ctx, int path) {
+  if (!ctx || path < 0 || path > 2) return HBG_ERR_INVALID;
+  ctx->interp_path = path;
   return HBG_OK;
 }
 
@@ -1176,6 +1387,112 @@ int hbg_allgather_block(hbg_ctx* ctx, const void* block, size_t bytes, void* con
   CU(cudaGetLastError());
   ctx->launches++;
   ctx->last_kernel = "gather_copy_kernel";
+  return HBG_OK;
+}
+
+namespace {
+int gather_signal(hbg_ctx* ctx, void* const* flags_peers, int world, int rank, int n_slots, int slot,
+                  int parts, GatherSignal* s) {
+  if (!flags_peers || world < 1 || world > 8 || rank < 0 || rank >= world || slot < 0 || slot >= n_slots ||
+      parts < 1)
+    return fail(ctx, HBG_ERR_INVALID, "bad gather signal argument");
+  memset(s, 0, sizeof *s);
+  for (int r = 0; r < world; r++) {
+    if (!flags_peers[r]) return fail(ctx, HBG_ERR_INVALID, "null flag pointer");
+    s->flags[r] = (unsigned*)flags_peers[r];
+  }
+  if (!ctx->gather_counter) return fail(ctx, HBG_ERR_NOMEM, "gather counter was not allocated");
+  s->counter = ctx->gather_counter;
+  s->error = ctx->gather_counter + 1;
+  s->slot_base = (unsigned)slot * 2u * (unsigned)world;
+  s->local_base = (unsigned)n_slots * 2u * (unsigned)world + 2u * (unsigned)slot;
+  s->parts = (unsigned)parts;
+  s->world = world;
+  s->rank = rank;
+  return HBG_OK;
+}
+}  // namespace
+
+int hbg_allgather_block_signal(hbg_ctx* ctx, const void* block, size_t bytes, void* const* peer_out,
+                               void* multicast_out, size_t offset_bytes, int world, int rank, int max_ctas,
+                               void* const* flags_peers, int n_slots, int slot, int parts, int first_part) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!block || !peer_out || world < 1 || world > 8 || (bytes & 15) || (offset_bytes & 15) || bytes == 0)
+    return fail(ctx, HBG_ERR_INVALID, "bad argument (sizes and offsets must be non-zero multiples of 16)");
+  CU(cudaSetDevice(ctx->device));
+  GatherSignal s;
+  int rc = gather_signal(ctx, flags_peers, world, rank, n_slots, slot, parts, &s);
+  if (rc) return rc;
+  s.first_part = first_part;
+  GatherDst g;
+  memset(&g, 0, sizeof(g));
+  g.world = world;
+  g.mc = (uint4*)multicast_out;
+  for (int r = 0; r < world; r++) {
+    if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
+    g.peers[r] = (uint4*)peer_out[r];
+  }
+  unsigned long long chunks = bytes / 16;
+  unsigned long long want = (chunks + 255) / 256;
+  unsigned ctas = (unsigned)(max_ctas > 0 ? max_ctas : 16);
+  if (ctas > want) ctas = (unsigned)want;
+  gather_copy_signal_kernel<<<ctas, 256, 0, ctx->stream>>>((const uint4*)block, g, offset_bytes / 16, chunks, s);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "gather_copy_signal_kernel";
+  return HBG_OK;
+}
+
+int hbg_allgather_block_ce(hbg_ctx* ctx, const void* block, size_t bytes, void* const* peer_out,
+                           size_t offset_bytes, int world, int rank, void* const* flags_peers, int n_slots,
+                           int slot, int parts, int first_part) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!block || !peer_out || world < 1 || world > 8 || bytes == 0)
+    return fail(ctx, HBG_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  GatherSignal s;
+  int rc = gather_signal(ctx, flags_peers, world, rank, n_slots, slot, parts, &s);
+  if (rc) return rc;
+  if (first_part) {
+    gather_wait_released_kernel<<<1, 32, 0, ctx->stream>>>(s);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
+  for (int i = 1; i < world; i++) {
+    const int r = (rank + i) % world;  // staggered: at any moment the ranks target different peers
+    if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
+    CU(cudaMemcpyAsync((uint8_t*)peer_out[r] + offset_bytes, block, bytes, cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  }
+  gather_signal_arrived_kernel<<<1, 32, 0, ctx->stream>>>(s);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "gather_signal_arrived_kernel";
+  return HBG_OK;
+}
+
+int hbg_gather_wait(hbg_ctx* ctx, void* const* flags_peers, int world, int rank, int n_slots, int slot,
+                    int parts) {
+  if (!ctx) return HBG_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  GatherSignal s;
+  int rc = gather_signal(ctx, flags_peers, world, rank, n_slots, slot, parts, &s);
+  if (rc) return rc;
+  gather_wait_kernel<<<1, 32, 0, ctx->stream>>>(s);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return HBG_OK;
+}
+
+int hbg_gather_release(hbg_ctx* ctx, void* const* flags_peers, int world, int rank, int n_slots, int slot) {
+  if (!ctx) return HBG_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  GatherSignal s;
+  int rc = gather_signal(ctx, flags_peers, world, rank, n_slots, slot, 1, &s);
+  if (rc) return rc;
+  gather_release_kernel<<<1, 32, 0, ctx->stream>>>(s);
+  CU(cudaGetLastError());
+  ctx->launches++;
   return HBG_OK;
 }
 
@@ -1321,9 +1638,26 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
                               const uint64_t* ys, size_t batch, uint64_t* out, int mem) {
   if (!ctx) return HBG_ERR_INVALID;
   if (!omega || k < 0 || (k && !zs)) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
-  if (k > 4096) return fail(ctx, HBG_ERR_UNSUPPORTED, "interpolation from more than 4096 points");
   CU(cudaSetDevice(ctx->device));
   { int trc = cache_trim(ctx); if (trc) return trc; }
+  // NTT-structured path (fnt_decode_step2): forced, or automatically for k > 128, where the
+  // O(k^3) host inverse of the matrix path and its O(k^2) products per row stop paying
+  if (k >= 1 && n >= 2 && (ctx->interp_path == 2 || (ctx->interp_path == 0 && k > 128))) {
+    FntConst fc;
+    int frc = fnt_constants(ctx, omega, n, zs, k, &fc);
+    if (frc == HBG_OK) {
+      if (batch == 0) return HBG_OK;
+      if (!out || !ys) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+      return run_rows(ctx, ys, (size_t)k * 32, out, (size_t)k * 32, batch, mem,
+                      [&](const void* di, void* dout, size_t rows) {
+                        return fnt_interpolate(ctx, fc, n, k, di, rows, dout);
+                      });
+    }
+    if (frc != HBG_ERR_UNSUPPORTED || ctx->interp_path == 2) return frc;
+  }
+  if (k > 4096)
+    return fail(ctx, HBG_ERR_UNSUPPORTED, "matrix-path interpolation from more than 4096 points "
+                                          "(this field has no root of unity for the NTT path)");
   const void* d_m = nullptr;
   const std::string key = make_key("finv", omega, 32, zs, (size_t)k * 4, n, k);
   int rc = interp_matrix(ctx, key, k, &d_m,

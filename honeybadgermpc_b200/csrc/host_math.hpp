@@ -227,6 +227,30 @@ inline std::vector<Fe> build_from_roots(const HostField& f, const std::vector<Fe
   return a;
 }
 
+// In-place radix-2 NTT on the host (Montgomery-form values): a[i] <- sum_j a[j] w^(ij),
+// len(a) = n a power of two, w a primitive n-th root (Montgomery form).  Constants only.
+inline void host_ntt(const HostField& f, std::vector<Fe>& a, const Fe& w) {
+  const size_t n = a.size();
+  for (size_t i = 1, j = 0; i < n; i++) {  // bit reversal
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const Fe wl = f.pow_u64(w, (uint64_t)(n / len));
+    for (size_t i = 0; i < n; i += len) {
+      Fe cur = f.one();
+      for (size_t j = 0; j < len / 2; j++) {
+        const Fe u = a[i + j], v = f.mul(a[i + j + len / 2], cur);
+        a[i + j] = f.add(u, v);
+        a[i + j + len / 2] = f.sub(u, v);
+        cur = f.mul(cur, wl);
+      }
+    }
+  }
+}
+
 inline Fe horner(const HostField& f, const std::vector<Fe>& a, const Fe& x) {
   Fe acc = fe_zero();
   for (size_t i = a.size(); i-- > 0;) acc = f.add(f.mul(acc, x), a[i]);

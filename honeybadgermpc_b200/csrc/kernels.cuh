@@ -283,6 +283,136 @@ __global__ void __launch_bounds__(256) gather_copy_kernel(const uint4* src, Gath
   }
 }
 
+// The same copy with the slot hand-over done by flags in symmetric memory instead of
+// host-issued barriers.  Every rank owns a flag array (uint32, zero-initialised), mapped
+// into every process:
+//   arrived [slot][r]  = how many blocks rank r has delivered into MY buffer of that slot,
+//                        counted over the whole run (monotonic)
+//   released[slot][r]  = how many fills of that slot rank r has finished reading
+// plus two words per slot that only the owner touches: sent (blocks this rank has copied
+// out for the slot) and waited (fills this rank has consumed).  Every value a kernel waits
+// for or publishes is derived from those device-side counters, never from a kernel
+// argument, so a CUDA graph of these launches can be replayed any number of times.
+//   copy kernel:   first part of a fill: wait until every rank has released the previous
+//                  fill; copy; all CTAs fence.sys; the last CTA (device counter) bumps
+//                  `sent` and publishes it in arrived[slot][me] on every rank (st.release.sys)
+//   wait kernel:   until arrived[slot][r] >= (waited + 1) * parts for every r
+//   release kernel: waited += 1, published in released[slot][me] on every rank
+// Waits are bounded: a dead peer sets *error instead of hanging the GPU.
+struct GatherSignal {
+  unsigned* flags[8];      // every rank's flag array as mapped here; flags[rank] is the local one
+  unsigned* counter;       // device word, 0 between launches (last-CTA detection)
+  unsigned* error;
+  unsigned slot_base;      // index of arrived[slot][0]; released[slot][0] is at slot_base + world
+  unsigned local_base;     // index of this slot's {sent, waited} pair
+  unsigned parts;          // blocks per rank and fill
+  int first_part;          // copy kernel: wait for the release of the previous fill
+  int world, rank;
+};
+
+HB_D unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+HB_D void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// spin until *p >= want (32-bit counters compared modulo 2^32); false on time-out (~2 s)
+HB_D bool spin_until(const unsigned* p, unsigned want, unsigned* error) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - want) < 0) {
+    if (clock64() - t0 > 4000000000ll) {
+      if (error) atomicExch(error, 2u);
+      return false;
+    }
+    __nanosleep(64);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) gather_copy_signal_kernel(const uint4* src, GatherDst g,
+                                                                 unsigned long long chunk0,
+                                                                 unsigned long long chunks, GatherSignal s) {
+  unsigned* local = s.flags[s.rank];
+  // `sent` only changes when the last CTA of this launch finishes, i.e. after every CTA read it
+  const unsigned sent = ld_acquire_sys(local + s.local_base);
+  if (s.first_part) {
+    if (threadIdx.x < (unsigned)s.world)
+      spin_until(local + s.slot_base + s.world + threadIdx.x, sent / s.parts, s.error);
+    __syncthreads();
+  }
+  // four independent 16-byte loads in flight per thread before the (remote) stores
+  const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+  for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < chunks; q += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (q + u * stride < chunks) v[u] = src[q + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const unsigned long long qq = q + u * stride;
+      if (qq >= chunks) break;
+      if (g.mc) {
+        st_multimem(g.mc + chunk0 + qq, v[u]);
+      } else {
+        for (int w = 0; w < g.world; w++) g.peers[w][chunk0 + qq] = v[u];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(s.counter, 1u);
+    if (done == gridDim.x - 1) {  // every CTA's stores are fenced: publish
+      *s.counter = 0;
+      st_release_sys(local + s.local_base, sent + 1);
+      __threadfence_system();
+      for (int w = 0; w < s.world; w++) st_release_sys(s.flags[w] + s.slot_base + s.rank, sent + 1);
+    }
+  }
+}
+
+// The hand-over around a copy done by the copy engines (cudaMemcpyAsync to the peers'
+// buffers, stream-ordered between these two one-warp kernels):
+// before -- first part of a fill: wait until every rank has released the previous fill
+__global__ void gather_wait_released_kernel(GatherSignal s) {
+  unsigned* local = s.flags[s.rank];
+  const unsigned sent = ld_acquire_sys(local + s.local_base);
+  if (threadIdx.x < (unsigned)s.world)
+    spin_until(local + s.slot_base + s.world + threadIdx.x, sent / s.parts, s.error);
+}
+
+// after -- one more block of this rank has landed everywhere: count it and tell every rank
+__global__ void gather_signal_arrived_kernel(GatherSignal s) {
+  unsigned* local = s.flags[s.rank];
+  const unsigned sent = ld_acquire_sys(local + s.local_base) + 1;
+  __syncwarp();
+  if (threadIdx.x == 0) st_release_sys(local + s.local_base, sent);
+  __threadfence_system();
+  if (threadIdx.x < (unsigned)s.world) st_release_sys(s.flags[threadIdx.x] + s.slot_base + s.rank, sent);
+}
+
+// consumer side: wait until every rank's blocks of the next fill have landed here
+__global__ void gather_wait_kernel(GatherSignal s) {
+  unsigned* local = s.flags[s.rank];
+  const unsigned waited = ld_acquire_sys(local + s.local_base + 1);
+  if (threadIdx.x < (unsigned)s.world)
+    spin_until(local + s.slot_base + threadIdx.x, (waited + 1) * s.parts, s.error);
+}
+
+// consumer side: this rank is done reading the fill
+__global__ void gather_release_kernel(GatherSignal s) {
+  unsigned* local = s.flags[s.rank];
+  const unsigned waited = ld_acquire_sys(local + s.local_base + 1) + 1;
+  __syncwarp();
+  if (threadIdx.x == 0) st_release_sys(local + s.local_base + 1, waited);
+  if (threadIdx.x < (unsigned)s.world)
+    st_release_sys(s.flags[threadIdx.x] + s.slot_base + s.world + s.rank, waited);
+}
+
 // ---------------------------------------------------------------------------
 // device-resident IncrementalDecoder (reed_solomon.py:305-331): columns live as
 // colbuf[n][batch]; these two kernels are pure data movement / comparison.
@@ -323,6 +453,59 @@ __global__ void __launch_bounds__(256) compare_columns_kernel(const uint4* rows,
     const bool same = x0.x == y0.x && x0.y == y0.y && x0.z == y0.z && x0.w == y0.w && x1.x == y1.x &&
                       x1.y == y1.y && x1.z == y1.z && x1.w == y1.w;
     if (!same) flags[j] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// NTT-structured interpolation, device side of fnt_decode_step2
+// (rsdecode_impl.h:226-265): elementwise pieces around the NTT launches.
+// ---------------------------------------------------------------------------
+struct FntArgs {
+  const uint4* in;     // [batch][k]   or  [batch][m]
+  uint4* out;          // see each kernel
+  const uint4* cst;    // Montgomery-form constants (per column)
+  const int* zs;       // scatter positions (device), k entries
+  unsigned long long batch;
+  int k, n, m;
+};
+
+// N[b][zs[i]] = ys[b][i] * (1 / A'(x_i)); `out` ([batch][n]) was zeroed beforehand
+template <class F>
+__global__ void __launch_bounds__(256) fnt_scale_scatter_kernel(FntArgs a) {
+  const unsigned long long total = a.batch * (unsigned)a.k;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * 256) {
+    const unsigned long long b = t / (unsigned)a.k;
+    const int i = (int)(t - b * (unsigned)a.k);
+    const Fe y = ld_fe(a.in + 2ull * t);
+    const Fe d = ld_fe(a.cst + 2 * i);
+    st_fe(a.out + 2ull * (b * (unsigned)a.n + (unsigned)a.zs[i]), mont_mul<F>(y, d));
+  }
+}
+
+// Q[b][j] = -R[b][(j + 1) % n], j < k; R has kr = min(k + 1, n) entries per row
+template <class F>
+__global__ void __launch_bounds__(256) fnt_shift_negate_kernel(FntArgs a) {
+  const unsigned long long total = a.batch * (unsigned)a.k;
+  const int kr = a.k + 1 < a.n ? a.k + 1 : a.n;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * 256) {
+    const unsigned long long b = t / (unsigned)a.k;
+    const int j = (int)(t - b * (unsigned)a.k);
+    const Fe r = ld_fe(a.in + 2ull * (b * (unsigned)kr + (unsigned)((j + 1) % a.n)));
+    st_fe(a.out + 2ull * t, fe_neg<F>(r));
+  }
+}
+
+// buf[b][i] *= cst[i], i < m (in place)
+template <class F>
+__global__ void __launch_bounds__(256) fnt_pointwise_kernel(FntArgs a) {
+  const unsigned long long total = a.batch * (unsigned)a.m;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * 256) {
+    const int i = (int)(t % (unsigned)a.m);
+    const Fe v = ld_fe(a.in + 2ull * t);
+    st_fe(a.out + 2ull * t, mont_mul<F>(v, ld_fe(a.cst + 2 * i)));
   }
 }
 

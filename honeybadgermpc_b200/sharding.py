@@ -84,64 +84,91 @@ class ShardedReconstructor:
     domain.  ``depth`` gather slots rotate, so up to ``depth`` steps are in
     flight.  ``gather``:
 
-      ``"auto"``   fused into the kernel epilogue, through the multicast address
-                   when there is one, else peer stores
-      ``"p2p"``    fused, peer stores only
-      ``"copy"``   local store + side-stream copy kernel (``hbg_allgather_block``)
-      ``"nccl"``   local store + ``all_gather_into_tensor`` on NCCL's stream
+      ``"auto"``     (= ``"ce"``) the interpolation kernel writes its block into its own
+                     slot of the local gather buffer; on a side stream the COPY ENGINES
+                     push it to every peer (``hbg_allgather_block_ce``: one
+                     ``cudaMemcpyAsync`` per peer into the symmetric-memory mapping, no
+                     SM touches the payload) and the slot hand-over runs on DEVICE flags
+                     in symmetric memory (``hbg_gather_wait`` / ``hbg_gather_release``):
+                     no host-issued barrier, nothing holds compute SMs while NVLink drains
+      ``"mc"``       the same with a copy KERNEL storing through the NVSwitch multicast
+                     address (``multimem.st``: the block leaves this GPU once and the
+                     switch replicates it; ``hbg_allgather_block_signal``)
+      ``"p2p"``      the copy kernel with peer stores only
+      ``"fused"``    the kernel epilogue stores into every rank's buffer itself
+                     (``hbg_fft_batch_interpolate_allgather``), hand-over by two
+                     symmetric-memory barriers per step on the side stream
+      ``"copy"``     copy kernel + the two barriers (round 1's protocol)
+      ``"nccl"``     local store + ``all_gather_into_tensor`` on NCCL's stream
 
     ``open(y_ptr)`` enqueues one step and returns its slot; ``wait(slot)``
     makes the caller's current stream wait for the gathered result
-    ``gathered[slot]`` (``int64[world * rows, k, 4]``); ``release(slot)`` hands
-    the slot back."""
+    ``gathered[slot]`` (``int64[world * parts * rows, k, 4]``); ``release(slot)``
+    hands the slot back (``finish(slot)`` = both, on an internal stream: what a
+    producer-only benchmark calls).
+
+    ``parts`` > 1: a slot is filled by ``parts`` consecutive steps of ``rows``
+    polynomials each (step ``part`` of rank r lands at row ``(r * parts + part) * rows``),
+    so the gather of one piece overlaps the interpolation of the next -- the shape of a
+    strong-scaling job where the whole batch is one result (BASELINE configs[4])."""
 
     def __init__(self, modulus, omega, order, zs, rows, group=None, device=None, depth=3, gather="auto",
-                 copy_ctas=16):
+                 copy_ctas=64, parts=1):
         import numpy as np
 
         self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self.rows, self.k, self.order = int(rows), len(zs), int(order)
+        self.rows, self.k, self.order, self.parts = int(rows), len(zs), int(order), int(parts)
         self.omega = np.ascontiguousarray(omega, dtype=np.uint64)
         self.zs = np.ascontiguousarray(zs, dtype=np.int32)
         self.copy_ctas = copy_ctas
+        mk_stream = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
+        self.stream, self.side, self.sync = mk_stream(), mk_stream(), mk_stream()
         self.ctx = _native.Context(modulus, device=self.device.index)
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.side = torch.cuda.Stream(device=self.device)
-        self.ctx.set_stream(self.stream.cuda_stream)
         self.side_ctx = _native.Context(modulus, device=self.device.index)
+        self.sync_ctx = _native.Context(modulus, device=self.device.index)
+        self.user_ctx = _native.Context(modulus, device=self.device.index)  # wait()/release() on caller streams
+        self.ctx.set_stream(self.stream.cuda_stream)
         self.side_ctx.set_stream(self.side.cuda_stream)
+        self.sync_ctx.set_stream(self.sync.cuda_stream)
         self.block_bytes = self.rows * self.k * 32
-        self.handles, self.gathered = [], []
+        self.handles, self.gathered, self.flag_handle, self.flags = [], [], None, None
         self.mode = "nccl" if gather == "nccl" else None
+        shape = (self.world * self.parts * self.rows, self.k, 4)
         if self.world > 1 and self.mode is None:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
                 for _ in range(depth):
-                    buf = symm_mem.empty((self.world * self.rows, self.k, 4), dtype=torch.int64,
-                                         device=self.device)
+                    buf = symm_mem.empty(shape, dtype=torch.int64, device=self.device)
                     self.handles.append(symm_mem.rendezvous(buf, self.group))
                     self.gathered.append(buf)
+                self.flags = symm_mem.empty((max(64, depth * (2 * self.world + 2)),), dtype=torch.int32,
+                                            device=self.device)
+                self.flags.zero_()
+                self.flag_handle = symm_mem.rendezvous(self.flags, self.group)
+                torch.cuda.synchronize(self.device)
+                dist.barrier(self.group)  # every rank's flags are zero before anyone signals
                 mc = int(getattr(self.handles[0], "multicast_ptr", 0) or 0)
-                if gather == "copy":
-                    self.mode = "multimem-copy" if mc else "p2p-copy"
-                elif gather == "auto":
-                    self.mode = "fused-multimem" if mc else "fused-p2p"
-                else:
-                    self.mode = "fused-p2p"
+                self.mode = {"auto": "ce-copy-signal", "ce": "ce-copy-signal",
+                             "mc": "multimem-copy-signal" if mc else "p2p-copy-signal",
+                             "p2p": "p2p-copy-signal",
+                             "fused": "fused-multimem" if mc else "fused-p2p",
+                             "copy": "multimem-copy" if mc else "p2p-copy"}[gather]
             except Exception as exc:  # noqa: BLE001 - no symmetric memory on this build / fabric
                 self.fallback_reason = repr(exc)
                 self.handles, self.gathered, self.mode = [], [], "nccl"
         if not self.gathered:
             self.mode = "nccl" if self.world > 1 else "local"
-            self.gathered = [torch.empty((self.world * self.rows, self.k, 4), dtype=torch.int64,
-                                         device=self.device) for _ in range(depth)]
+            self.gathered = [torch.empty(shape, dtype=torch.int64, device=self.device) for _ in range(depth)]
         self.depth = len(self.gathered)
+        self.signal = self.mode.endswith("signal")
         self.peers = [_native.Context.peer_array(list(h.buffer_ptrs)) for h in self.handles]
         self.mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
+        self.flag_peers = _native.Context.peer_array(list(self.flag_handle.buffer_ptrs)) \
+            if self.flag_handle is not None else None
         mk = torch.cuda.Event
         self.ready_ev = [mk() for _ in range(self.depth)]
         self.written_ev = [mk() for _ in range(self.depth)]
@@ -151,68 +178,111 @@ class ShardedReconstructor:
         self.step_no = 0
 
     # -- one step -----------------------------------------------------------------
-    def own_block_ptr(self, slot):
-        return self.gathered[slot].data_ptr() + self.rank * self.block_bytes
+    def own_block_ptr(self, slot, part=0):
+        return self.gathered[slot].data_ptr() + (self.rank * self.parts + part) * self.block_bytes
 
-    def open(self, y_ptr, slot=None):
+    def open(self, y_ptr, slot=None, part=0):
         """enqueue: interpolate ``rows`` polynomials from the device array at ``y_ptr``
         (``[rows, k, 4]`` uint64) and all-gather the result into slot ``slot``"""
         if slot is None:
-            slot = self.step_no % self.depth
+            slot = (self.step_no // self.parts) % self.depth
         self.step_no += 1
         fused = self.mode.startswith("fused")
-        if self.handles:
+        first, last = part == 0, part == self.parts - 1
+        block_row = self.rank * self.parts + part  # in units of `rows`
+        if first and self.released_ev[slot] is not None:  # the local reader of the previous fill
+            self.stream.wait_event(self.released_ev[slot])
+        if self.handles and first and not self.signal:
             # (1) everyone has released slot `slot`: its previous contents may be overwritten
             with torch.cuda.stream(self.side):
-                if self.released_ev[slot] is not None:
-                    self.side.wait_event(self.released_ev[slot])
                 self.handles[slot].barrier(channel=0)
                 self.ready_ev[slot].record(self.side)
             self.stream.wait_event(self.ready_ev[slot])
-        elif self.pending[slot] is not None:
+        elif not self.handles and first and self.pending[slot] is not None:
             self.pending[slot].wait()
             self.pending[slot] = None
         if fused:
-            self.ctx.fft_batch_interpolate_allgather(
-                self.omega, self.order, self.zs, y_ptr, self.rows, self.peers[slot],
-                self.mc[slot] if self.mode == "fused-multimem" else 0, self.rank)
+            # rank-relative placement: the kernel stores row r at gather_row0 + r with
+            # gather_row0 = rank * rows, so shift the peer bases by the part's offset
+            base = (block_row - self.rank) * self.block_bytes
+            peers = self.peers[slot] if base == 0 else _native.Context.peer_array(
+                [int(p) + base for p in self.handles[slot].buffer_ptrs])
+            mc = self.mc[slot] + base if (self.mode == "fused-multimem") else 0
+            self.ctx.fft_batch_interpolate_allgather(self.omega, self.order, self.zs, y_ptr, self.rows,
+                                                     peers, mc, self.rank)
         else:
             self.ctx.fft_batch_interpolate(self.omega, self.order, self.zs, y_ptr, self.rows,
-                                           self.own_block_ptr(slot), _native.MEM_DEVICE)
+                                           self.own_block_ptr(slot, part), _native.MEM_DEVICE)
         if self.handles:
             self.written_ev[slot].record(self.stream)
-            with torch.cuda.stream(self.side):
-                self.side.wait_event(self.written_ev[slot])
-                if not fused:
-                    self.side_ctx.allgather_block(
-                        self.own_block_ptr(slot), self.block_bytes, self.peers[slot],
-                        self.mc[slot] if self.mode == "multimem-copy" else 0,
-                        self.rank * self.block_bytes, self.copy_ctas)
-                # (2) every rank's block has landed in every buffer
-                self.handles[slot].barrier(channel=1)
-                self.done_ev[slot].record(self.side)
+            self.side.wait_event(self.written_ev[slot])
+            use_mc = self.mc[slot] if self.mode.startswith("multimem") else 0
+            if self.mode == "ce-copy-signal":
+                self.side_ctx.allgather_block_ce(
+                    self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot],
+                    block_row * self.block_bytes, self.rank, self.flag_peers, self.depth, slot, self.parts,
+                    first)
+            elif self.signal:
+                self.side_ctx.allgather_block_signal(
+                    self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot], use_mc,
+                    block_row * self.block_bytes, self.rank, self.copy_ctas, self.flag_peers, self.depth,
+                    slot, self.parts, first)
+            else:
+                with torch.cuda.stream(self.side):
+                    if not fused:
+                        self.side_ctx.allgather_block(
+                            self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot], use_mc,
+                            block_row * self.block_bytes, self.copy_ctas)
+                    if last:
+                        # (2) every rank's blocks have landed in every buffer
+                        self.handles[slot].barrier(channel=1)
+                        self.done_ev[slot].record(self.side)
         elif self.world > 1:
-            with torch.cuda.stream(self.stream):
-                own = self.gathered[slot][self.rank * self.rows:(self.rank + 1) * self.rows]
-                self.pending[slot] = dist.all_gather_into_tensor(self.gathered[slot], own, group=self.group,
-                                                                 async_op=True)
-        else:
+            if last:
+                with torch.cuda.stream(self.stream):
+                    per = self.parts * self.rows
+                    own = self.gathered[slot][self.rank * per:(self.rank + 1) * per]
+                    self.pending[slot] = dist.all_gather_into_tensor(self.gathered[slot], own,
+                                                                     group=self.group, async_op=True)
+        elif last:
             self.done_ev[slot].record(self.stream)
         return slot
 
+    def _wait_on(self, ctx, stream, slot):
+        stream.wait_event(self.written_ev[slot])  # this rank's own block
+        ctx.gather_wait(self.flag_peers, self.rank, self.depth, slot, self.parts)
+
     def wait(self, slot):
         """the caller's current stream waits for slot ``slot`` to be complete"""
+        cur = torch.cuda.current_stream(self.device)
         if self.pending[slot] is not None:
             self.pending[slot].wait()
             self.pending[slot] = None
+        elif self.signal:
+            self.user_ctx.set_stream(cur.cuda_stream)
+            self._wait_on(self.user_ctx, cur, slot)
         elif self.handles or self.world == 1:
-            torch.cuda.current_stream(self.device).wait_event(self.done_ev[slot])
+            cur.wait_event(self.done_ev[slot])
 
     def release(self, slot):
         """the caller's current stream is done reading slot ``slot``"""
+        cur = torch.cuda.current_stream(self.device)
+        if self.signal:
+            self.user_ctx.set_stream(cur.cuda_stream)
+            self.user_ctx.gather_release(self.flag_peers, self.rank, self.depth, slot)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
+        ev.record(cur)
         self.released_ev[slot] = ev
+
+    def finish(self, slot):
+        """wait + release on an internal stream (a producer with no reader of its own: the
+        benchmark).  In the barrier modes the hand-over is already part of ``open``."""
+        if not self.signal:
+            return
+        self._wait_on(self.sync_ctx, self.sync, slot)
+        self.sync_ctx.gather_release(self.flag_peers, self.rank, self.depth, slot)
+        self.done_ev[slot].record(self.sync)
+        self.released_ev[slot] = self.done_ev[slot]  # the next fill's kernel must not start earlier
 
     def drain(self):
         for slot in range(self.depth):
@@ -221,28 +291,42 @@ class ShardedReconstructor:
                 self.pending[slot] = None
         self.stream.synchronize()
         self.side.synchronize()
+        self.sync.synchronize()
 
     # -- CUDA graph of a sequence of steps ----------------------------------------
-    def capture(self, y_ptrs, begin=None, extra=None, finish=None):
-        """Capture ``len(y_ptrs)`` consecutive steps (slot i % depth) into one CUDA
+    def capture(self, y_ptrs, begin=None, extra=None, finish=None, auto_finish=True):
+        """Capture ``len(y_ptrs)`` consecutive steps (slot (i // parts) % depth) into one CUDA
         graph.  ``begin()`` may fork further streams from ``self.stream``, ``extra(i)``
-        enqueue more work per step on them, ``finish()`` must join them back.  Returns
-        the ``torch.cuda.CUDAGraph``; replaying it costs the host one launch.  NCCL
-        mode is not capturable (returns ``None``)."""
+        enqueue more work per step on them, ``finish()`` must join them back.  With
+        ``auto_finish`` every filled slot is waited for and released inside the graph.
+        Returns the ``torch.cuda.CUDAGraph``; replaying it costs the host one launch (the
+        hand-over flags are counted on the device, so replays need no host bookkeeping).
+        NCCL mode is not capturable (returns ``None``)."""
         if self.mode == "nccl":
             return None
+        # warm-up outside the capture: the first call for a point set builds its constants
+        # (cudaMalloc + copy) and opts the kernel in to large shared memory, none of which may
+        # happen while a stream is capturing.  Purely local: no flag is touched.
+        self.ctx.fft_batch_interpolate(self.omega, self.order, self.zs, y_ptrs[0], self.rows,
+                                       self.own_block_ptr(0, 0), _native.MEM_DEVICE)
         self.drain()
         graph = torch.cuda.CUDAGraph()
         self.released_ev = [None] * self.depth
         with torch.cuda.graph(graph, stream=self.stream, capture_error_mode="thread_local"):
-            self.side.wait_stream(self.stream)  # fork: the side stream is part of the capture
+            self.side.wait_stream(self.stream)  # fork: the side streams are part of the capture
+            self.sync.wait_stream(self.stream)
             if begin is not None:
                 begin()
             for i, y in enumerate(y_ptrs):
                 if extra is not None:
                     extra(i)
-                self.open(y, slot=i % self.depth)
+                slot, part = (i // self.parts) % self.depth, i % self.parts
+                self.open(y, slot=slot, part=part)
+                if auto_finish and part == self.parts - 1:
+                    self.finish(slot)
             if finish is not None:
                 finish()
             self.stream.wait_stream(self.side)
+            self.stream.wait_stream(self.sync)
+        self.released_ev = [None] * self.depth  # events recorded inside a capture are not usable outside
         return graph

@@ -157,6 +157,38 @@ int hbg_allgather_block(hbg_ctx* ctx, const void* block, size_t bytes,
                         void* const* peer_out, void* multicast_out,
                         size_t offset_bytes, int world, int max_ctas);
 
+/* hbg_allgather_block with the slot hand-over on the device (no host-issued barrier).
+ * flags_peers[r] is rank r's flag array (uint32, symmetric memory, zero-initialised, at
+ * least n_slots * (2 * world + 2) entries) as mapped into this process.  Per slot it holds
+ * arrived[world] and released[world] (written by the peers) and, after all slots, the
+ * owner's own {sent, waited} counters; every value waited for or published is derived
+ * from those device-side counters, so a CUDA graph of these calls can be replayed.
+ *   hbg_allgather_block_signal: (first_part != 0: wait until every rank has released the
+ *     previous fill of the slot;) copy; publish "one more block of mine has landed" on every
+ *     rank.  A fill consists of `parts` blocks per rank.
+ *   hbg_gather_wait:    one-warp kernel, returns when every rank's `parts` blocks of the
+ *     next unconsumed fill have landed here.
+ *   hbg_gather_release: marks that fill consumed and tells every rank.
+ * Waits time out after ~2 s (a dead peer must not hang the GPU). */
+int hbg_allgather_block_signal(hbg_ctx* ctx, const void* block, size_t bytes,
+                               void* const* peer_out, void* multicast_out,
+                               size_t offset_bytes, int world, int rank, int max_ctas,
+                               void* const* flags_peers, int n_slots, int slot,
+                               int parts, int first_part);
+int hbg_gather_wait(hbg_ctx* ctx, void* const* flags_peers, int world, int rank,
+                    int n_slots, int slot, int parts);
+/* The same copy on the COPY ENGINES (no SM touches the payload): when first_part != 0 a
+ * one-warp kernel first waits for the release of the slot's previous fill; then one
+ * cudaMemcpyAsync per peer (peer_out[r] + offset_bytes <- block; the local buffer already
+ * holds the block) and a one-warp kernel that publishes the arrival, all stream-ordered on
+ * the context's stream.  Unicast: world-1 copies of the block leave this GPU. */
+int hbg_allgather_block_ce(hbg_ctx* ctx, const void* block, size_t bytes,
+                           void* const* peer_out, size_t offset_bytes, int world, int rank,
+                           void* const* flags_peers, int n_slots, int slot,
+                           int parts, int first_part);
+int hbg_gather_release(hbg_ctx* ctx, void* const* flags_peers, int world, int rank,
+                       int n_slots, int slot);
+
 /* gao_interpolate(x, y, k, modulus, ...), pyx:389-439 + gao_interpolate /
  * gao_interpolate_fft / partial_gcd, rsdecode_impl.h:281-405 -- batched: every
  * row of ys is one received word on the SAME m points xs (erasures already
@@ -219,6 +251,12 @@ int hbg_compare_columns(hbg_ctx* ctx, const uint64_t* rows, int row_width, int c
                         const uint64_t* colbuf, size_t batch,
                         const int32_t* idx, int m,
                         int32_t* flags_dev, int32_t* flags_host);
+
+/* hbg_fft_batch_interpolate: 0 = automatic (the V^-1 matrix for k <= 128, the
+ * NTT-structured path of fnt_decode_step2 above), 1 = matrix, 2 = NTT-structured
+ * (HBG_ERR_UNSUPPORTED if the field lacks the root of unity it needs).  All paths
+ * return identical bits; the tests force each. */
+int hbg_ctx_set_interp_path(hbg_ctx* ctx, int path);
 
 /* Test hook: bound (bytes) of the per-context cache of device constants; when it
  * is exceeded the cache is dropped at the entry of the next call (default 256 MB). */

@@ -75,6 +75,16 @@ class OracleContext:
         if batch:
             _store(out, orc.fft_batch_interpolate(zs, _ints(ys), w, self.p, n))
 
+    def interpolate_reencode(self, xs_k, xs_all, ys, batch, out, mem=0):
+        self.launches += 1
+        xk, xa = _ints(xs_k), _ints(xs_all)
+        if len(set(xk)) != len(xk):
+            raise _native.SingularError("singular Vandermonde matrix")
+        if batch:
+            coeffs = orc.vandermonde_batch_interpolate(xk, _ints(ys), self.p)
+            ev = orc.vandermonde_batch_evaluate(xa, coeffs, self.p) if xa else [[] for _ in coeffs]
+            _store(out, [c + e for c, e in zip(coeffs, ev)])
+
     def gao_decode_batch(self, xs, k, ys, batch, coeffs, locator, loc_stride, loc_len, status, mem=0):
         self.launches += 1
         x = _ints(xs)

@@ -191,6 +191,72 @@ def test_tensor_core_path(ntl):
         ctx.set_matvec_path("auto")
 
 
+@pytest.mark.parametrize("r,k,batch", [(4, 6, 70), (4, 16, 9), (7, 43, 40), (7, 128, 5), (10, 342, 6),
+                                       (10, 129, 3), (12, 700, 2), (3, 1, 4), (5, 2, 3)])
+def test_fnt_interpolation_path(ntl, r, k, batch):
+    """The NTT-structured interpolation (fnt_decode_step1/2, rsdecode_impl.h:194-265: scale by
+    1/A'(x_i), scatter, inverse NTT, MulTrunc by A) against the oracle's restatement of the same
+    two steps and against the V^-1 matrix path: identical bits.  k = 342 / n = 1024 and
+    k = 700 / n = 4096 never form a k x k inverse."""
+    rng = random.Random(r * 1000 + k)
+    n = 2 ** r
+    omega = ROOTS_OF_UNITY[r] if r < len(ROOTS_OF_UNITY) else pow(7, (P - 1) // n, P)
+    zs = rng.sample(range(n), k)
+    ys = [[rng.randrange(P) for _ in range(k)] for _ in range(batch)]
+    ys[0] = [P - 1] * k
+    ctx = ntl._ctx(P)
+    try:
+        ctx.set_interp_path("fnt")
+        got = ntl.fft_batch_interpolate(zs, ys, omega, P, n)
+        assert ctx.last_kernel() == "fnt_decode_step2"
+        want = orc.fft_batch_interpolate(zs, ys[: min(batch, 3)], omega, P, n)
+        assert got[: len(want)] == want
+        if k <= 342:
+            ctx.set_interp_path("matrix")
+            assert ntl.fft_batch_interpolate(zs, ys, omega, P, n) == got
+        ctx.set_interp_path("auto")
+        assert ntl.fft_batch_interpolate(zs, ys, omega, P, n) == got
+        assert (ctx.last_kernel() == "fnt_decode_step2") == (k > 128)
+        # the interpolant really passes through the points
+        xs = [pow(omega, z, P) for z in zs[:4]]
+        for row, y in list(zip(got, ys))[:2]:
+            assert [orc.poly_eval(row, x, P) for x in xs] == y[:4]
+    finally:
+        ctx.set_interp_path("auto")
+
+
+def test_fnt_interpolation_other_fields(ntl):
+    # p = 257: every power-of-two order up to 256 exists; p = 13: order 4
+    rng = random.Random(2)
+    for p, w, n in ((257, 3, 256), (257, pow(3, 16, 257), 16), (13, 5, 4), (97, 8, 16)):
+        for k in (1, 2, min(n, 7), n // 2):
+            if k < 1:
+                continue
+            zs = rng.sample(range(n), k)
+            ys = [[rng.randrange(p) for _ in range(k)] for _ in range(5)]
+            ctx = ntl._ctx(p)
+            want = orc.fft_batch_interpolate(zs, ys, w, p, n)
+            try:
+                ctx.set_interp_path("fnt")
+                try:
+                    got = ntl.fft_batch_interpolate(zs, ys, w, p, n)
+                except NotImplementedError:
+                    # no root of unity of order >= 2k in this field: the automatic path must
+                    # fall back to the matrix silently
+                    ctx.set_interp_path("auto")
+                    got = ntl.fft_batch_interpolate(zs, ys, w, p, n)
+                assert got == want, (p, n, k)
+            finally:
+                ctx.set_interp_path("auto")
+    # repeated z: the reference divides by zero (inv(0) in fnt_decode_step1)
+    ntl._ctx(P).set_interp_path("fnt")
+    try:
+        with pytest.raises(ZeroDivisionError):
+            ntl.fft_batch_interpolate([1, 1], [[1, 2]], ROOTS_OF_UNITY[2], P, 4)
+    finally:
+        ntl._ctx(P).set_interp_path("auto")
+
+
 def test_fft_small_prime(ntl):
     # p = 13: omega = 5 has order 4 (tests/test_ntl.py:57-68); p = 257: order 256
     for path in ("matrix", "ntt"):

@@ -265,6 +265,15 @@ def test_incremental_decoder_device_resident(rs, monkeypatch):
         logging.disable(logging.NOTSET)
 
 
+def test_offline_callers_on_limb_path(rs):
+    """offline_randousha.py:47-53,72-78,99-121; progs/triple_refinement.py:36-88;
+    preprocessing.py:222-231 -- the compute steps on the kernels vs the oracle"""
+    import offline_cases
+
+    offline_cases.check_offline_callers(batch=37)
+    offline_cases.check_offline_callers(batch=700, seed=9)  # large enough for the tensor-core kernel
+
+
 # --- batch_reconstruct (tests/test_batch_reconstruction.py:12-170) -------------
 
 
@@ -405,12 +414,26 @@ def test_party_simulation_in_process(n, t, batch, omega):
     codecs = [party_sim.CudaCodec(P, n, use_omega_powers=omega)] * n  # one GPU plays every party
     for got, ok in party_sim.simulate_in_process(codecs, shares, t):
         assert ok and _limbs_to_ints(got) == secrets
-    # a wrong share of the last party is noticed by everyone (re-encode + compare)
+    # a wrong share of the last party is noticed by everyone (re-encode + compare) and, with
+    # t >= 1, corrected by the robust fallback (hbg_gao_decode_batch on device pointers)
     if n > t + 1:
         shares[n - 1] = shares[n - 1].clone()
         shares[n - 1][0, 0] += 1
-        res = party_sim.simulate_in_process(codecs, shares, t)
-        assert not any(ok for _, ok in res)
+        info = []
+        res = party_sim.simulate_in_process(codecs, shares, t, info=info)
+        if t == 0:
+            assert not any(ok for _, ok in res)
+        else:
+            for got, ok in res:
+                assert ok and _limbs_to_ints(got) == secrets
+            assert all(errs == [n - 1] and rounds == 1 for errs, rounds in info)
+            # t parties sending noise in both rounds
+            liars = tuple(range(1, 1 + t)) if n - 1 not in range(1, 1 + t) else tuple(range(t))
+            shares[n - 1][0, 0] -= 1
+            info = []
+            for got, ok in party_sim.simulate_in_process(codecs, shares, t, byzantine=liars, info=info):
+                assert ok and _limbs_to_ints(got) == secrets
+            assert all(errs == sorted(liars) and rounds == 2 for errs, rounds in info)
     torch.cuda.synchronize()
 
 

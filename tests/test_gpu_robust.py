@@ -181,6 +181,35 @@ def test_wb_vs_oracle_random(rs, p):
             assert got == want, (trial, n, k, z, row, want, got)
 
 
+def test_config3_n64_golden(rs):
+    """BASELINE configs[2]: n = 64, t = 21, up to t corrupted evaluations per word -- 36 words
+    decoded by the oracle's restatement of the reference's Welch-Berlekamp solver (about a
+    second per word; tests/golden/make_wb_n64_golden.py, cross-checked there against the
+    reference's own class) vs wb_kernel and gao_kernel, batched."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wb_n64_v1.json")
+    with open(path) as fh:
+        gold = json.load(fh)
+    n, t = gold["n"], gold["t"]
+    assert (n, t) == (64, 21) and len(gold["cases"]) >= 32
+    for omega in (False, True):
+        cases = [c for c in gold["cases"] if c["use_omega_powers"] == omega]
+        pt = _point(P, n, omega)
+        rows = [[int(v, 16) for v in c["received"]] for c in cases]
+        want = [([int(v, 16) for v in c["decoded"]], c["errors"]) for c in cases]
+        z = list(range(n))
+        assert rs.WelchBerlekampRobustDecoder(t, pt).robust_decode_batch(z, rows) == want
+        assert rs.GaoRobustDecoder(t, pt).robust_decode_batch(z, rows) == want
+        # a permuted arrival order of the parties changes nothing
+        perm = list(range(n))
+        random.Random(4).shuffle(perm)
+        prow = [[r[i] for i in perm] for r in rows[:6]]
+        assert rs.WelchBerlekampRobustDecoder(t, pt).robust_decode_batch(perm, prow) == want[:6]
+        assert rs.GaoRobustDecoder(t, pt).robust_decode_batch(perm, prow) == want[:6]
+
+
 def test_gao_equals_wb_when_decodable(rs):
     rng = random.Random(8)
     n, t = 16, 5

@@ -92,3 +92,11 @@ def test_opened_polynomial_and_sqrt():
     with pytest.raises(AssertionError):  # like the reference's assertion (field.py:175)
         GF(13)(2).sqrt()  # 2 is not a square mod 13
     assert (~f(3)) * 3 == 1 and f(10) // f(5) == 2 and f(P - 1).signed() == -1 and f(6).bit(1) == 1
+
+
+def test_offline_callers(rs):
+    """randousha / refine_triples / _write_polys compute steps on the limb path (CPU: the host
+    logic with the oracle behind the context; tests/test_gpu_protocol.py runs the kernels)"""
+    import offline_cases
+
+    offline_cases.check_offline_callers(batch=5)

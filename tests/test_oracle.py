@@ -122,3 +122,26 @@ def test_sympy_crosscheck():
     q, r = gf_div(rev(a), rev(b), P, ZZ)
     oq, orr = orc.poly_divrem(a, b, P)
     assert oq == [int(x) for x in reversed(q)] and orr == [int(x) for x in reversed(r)]
+
+
+def test_config3_n64_golden_matches_oracle():
+    """tests/golden/wb_n64_v1.json (n = 64, t = 21) is what the oracle's Welch-Berlekamp and Gao
+    produce: re-derive three words (the GPU suite checks the kernels against all 36)"""
+    import json
+    import os
+
+    from conftest import BLS12_381_R as p
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wb_n64_v1.json")) as fh:
+        gold = json.load(fh)
+    assert gold.get("cross_checked_with_reference") == 2
+    for case in (gold["cases"][0], gold["cases"][7], gold["cases"][-1]):
+        pt = orc.EvalPoint(p, gold["n"], case["use_omega_powers"])
+        word = [int(v, 16) for v in case["received"]]
+        want = ([int(v, 16) for v in case["decoded"]], case["errors"])
+        z = list(range(gold["n"]))
+        assert orc.gao_robust_decode(z, word, gold["n"], gold["t"] + 1, p, pt) == want
+    case = gold["cases"][3]
+    pt = orc.EvalPoint(p, gold["n"], case["use_omega_powers"])
+    assert orc.wb_robust_decode(list(range(64)), [int(v, 16) for v in case["received"]], 64, 22, p, pt) == \
+        ([int(v, 16) for v in case["decoded"]], case["errors"])

@@ -36,8 +36,29 @@ def to_ints(t):
     return [flat[i * w:(i + 1) * w] for i in range(t.shape[0])]
 
 
-class OracleCodec:
+class _OracleRobust:
+    """robust_decode of the codec interface (Gao over all n parties) by the oracle"""
+
+    def _points(self):
+        raise NotImplementedError
+
+    def robust_decode(self, rows, k):
+        xs = self._points()
+        coeffs, decoded, bad = [], [], []
+        for word in to_ints(rows):
+            dec, loc = orc.gao_interpolate(xs, word, k, self.p)
+            decoded.append(dec is not None)
+            coeffs.append(dec if dec is not None else [0] * k)
+            roots = [len(loc or []) > 1 and orc.poly_eval(loc, x, self.p) == 0 for x in xs]
+            bad.append(roots)
+        return to_limbs(coeffs), torch.tensor(decoded), torch.tensor(bad).reshape(len(coeffs), self.n)
+
+
+class OracleCodec(_OracleRobust):
     """the codec interface of party_sim on CPU tensors, computed by the oracle"""
+
+    def _points(self):
+        return self.xs
 
     def __init__(self, p, n):
         self.p, self.n = p, n
@@ -74,10 +95,11 @@ def _worker(rank, world, port, t, batch, corrupt, results):
         secrets, shares = make_shares(world, t, batch, seed=world * 100 + batch)
         mine = to_limbs([[v] for v in shares[rank]]).reshape(batch, 4)
         if corrupt and rank == world - 1:
-            mine[0, 0] += 1  # a wrong share: every party must notice (ok == False)
-        got, ok = party_sim.batch_reconstruct_collective(mine, t, OracleCodec(P, world))
+            mine[0, 0] += 1  # a wrong share: <= t faulty parties are corrected by the robust fallback
+        info = {}
+        got, ok = party_sim.batch_reconstruct_collective(mine, t, OracleCodec(P, world), info=info)
         opened = [r[0] for r in to_ints(got.reshape(batch, 1, 4))]
-        results[rank] = (opened == secrets, ok)
+        results[rank] = (opened == secrets, ok, info["errors"])
     finally:
         dist.destroy_process_group()
 
@@ -97,14 +119,18 @@ def test_parties_as_ranks_gloo(world, t, batch, corrupt):
         assert p.exitcode == 0
     res = dict(results)
     assert set(res) == set(range(world))
-    if corrupt:
-        assert all(not ok for _, ok in res.values())
-    else:
-        assert all(match and ok for match, ok in res.values())
+    assert all(match and ok for match, ok, _ in res.values())
+    for r, (_, _, errors) in res.items():
+        # R1 carries the lie (party world-1's chunk polynomial is off in one coefficient); by R2
+        # every honest party publishes corrected values, so only R1 needs the robust decoder
+        assert errors == ([world - 1] if corrupt else [])
 
 
-class OracleOmegaCodec:
+class OracleOmegaCodec(_OracleRobust):
     """omega-power points (FFT encode / interpolate of the oracle)"""
+
+    def _points(self):
+        return [self.pt(i) for i in range(self.n)]
 
     def __init__(self, p, n):
         self.p, self.n = p, n
@@ -129,7 +155,15 @@ def test_in_process_simulation_omega_points(n, t, batch):
     for got, ok in party_sim.simulate_in_process([codec] * n, per_party, t):
         assert ok and [r[0] for r in to_ints(got.reshape(batch, 1, 4))] == secrets
     per_party[n - 1][0, 0] += 1
-    assert not any(ok for _, ok in party_sim.simulate_in_process([codec] * n, per_party, t))
+    info = []
+    for got, ok in party_sim.simulate_in_process([codec] * n, per_party, t, info=info):
+        assert ok and [r[0] for r in to_ints(got.reshape(batch, 1, 4))] == secrets
+    assert all(errs == [n - 1] and rounds == 1 for errs, rounds in info)
+    # a party that sends noise in both rounds
+    info = []
+    for j, (got, ok) in enumerate(party_sim.simulate_in_process([codec] * n, per_party, t, byzantine=(2,), info=info)):
+        assert ok and [r[0] for r in to_ints(got.reshape(batch, 1, 4))] == secrets
+    assert all(errs == [2, n - 1] and rounds == 2 for errs, rounds in info)
 
 
 def test_in_process_simulation_matches():

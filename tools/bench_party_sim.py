@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-check", action="store_true", help="skip the re-encode + compare of both rounds")
+    ap.add_argument("--byzantine", type=int, default=0,
+                    help="the last K ranks (K <= t) send noise in both rounds: every opening takes the "
+                         "robust-decoder fallback")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -43,15 +46,21 @@ def main():
     dc = torch.from_numpy(coeffs).cuda()
     shares = codec.encode(dc)[:, rank].contiguous()        # f_b(x_rank)
     secrets = dc[:, 0].contiguous()
+    assert args.byzantine <= t, "at most t faulty parties"
+    bad = rank >= world - args.byzantine
+    info = {}
+    kw = dict(check=not args.no_check, byzantine=bad, info=info)
     for _ in range(args.warmup):
-        got, ok = party_sim.batch_reconstruct_collective(shares, t, codec, check=not args.no_check)
-    assert ok and torch.equal(got, secrets), "opening failed"
+        got, ok = party_sim.batch_reconstruct_collective(shares, t, codec, **kw)
+    if not bad:
+        assert ok and torch.equal(got, secrets), "opening failed"
+        assert info["errors"] == list(range(world - args.byzantine, world)), info
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        got, ok = party_sim.batch_reconstruct_collective(shares, t, codec, check=not args.no_check)
+        got, ok = party_sim.batch_reconstruct_collective(shares, t, codec, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda", dtype=torch.float64)
@@ -60,7 +69,8 @@ def main():
         print(json.dumps({"tool": "bench_party_sim", "n_parties": n, "t": t, "shares_per_open": args.batch,
                           "ms_per_open": float(ms.item()),
                           "shares_opened_per_s": args.batch / (float(ms.item()) * 1e-3),
-                          "check": not args.no_check,
+                          "check": not args.no_check, "byzantine_parties": args.byzantine,
+                          "robust_rounds_per_open": info.get("robust_rounds"), "errors_found": info.get("errors"),
                           "note": "every party (GPU) learns all opened values; R1 all-to-all + R2 all-gather"}))
     dist.barrier()
     dist.destroy_process_group()
