@@ -393,7 +393,7 @@ def run_b200(args):
     # ---- the timed region: `unit` = lcm(sets, depth) consecutive steps captured into ONE CUDA
     # graph (the Python step loop costs ~20 us per step, more than the GPU work of a step),
     # replayed until at least --steps steps AND --min-ms of device time have run
-    unit = int(sets * depth // np.gcd(sets, depth))
+    unit = int(sets * depth // np.gcd(sets, depth)) * args.graph_units
     graph = None
     if not args.no_graph:
         try:
@@ -668,6 +668,9 @@ def main():
     ap.add_argument("--cfg5-passes", type=int, default=5)
     ap.add_argument("--min-ms", type=float, default=60.0,
                     help="the timed region is extended (more steps) until it lasts at least this long")
+    ap.add_argument("--graph-units", type=int, default=4,
+                    help="steps per captured graph = lcm(sets, slots) x this (a replay ends with a join of "
+                         "all streams, i.e. drains the gather pipeline once)")
     ap.add_argument("--no-graph", action="store_true", help="eager Python step loop instead of a CUDA graph")
     ap.add_argument("--matvec-path", default="auto",
                     help="auto (tensor-core kernel) | no-tc (the IMAD kernels of round 1) | ...")

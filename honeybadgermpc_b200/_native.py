@@ -218,7 +218,7 @@ class Context:
         return self.lib.hbg_ctx_last_kernel(self.handle).decode()
 
     def set_fft_path(self, path):
-        self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2, "ntt-smem": 3, "ntt-split": 4, "ntt-bal": 5}[path]))
+        self._check(self.lib.hbg_ctx_set_fft_path(self.handle, {"auto": 0, "matrix": 1, "ntt": 2, "ntt-smem": 3, "ntt-split": 4, "ntt-bal": 5, "tc-split": 6}[path]))
 
     def set_matvec_path(self, path):
         self._check(self.lib.hbg_ctx_set_matvec_path(

@@ -47,13 +47,16 @@ struct hbg_ctx {
   bool is_bls = false;
   int fft_path = 0;     // 0 auto, 1 matrix, 2 ntt, 3 ntt through the generic smem kernel,
                         // 4 ntt with the register-resident split kernel for n = 16,
-                        // 5 ntt, n = 16 with the balanced (hand-over) form of the 4-point-group kernel
+                        // 5 ntt, n = 16 with the balanced (hand-over) form of the 4-point-group kernel,
+                        // 6 matrix on the tensor cores in the radix-2 split form (where it fits)
   int matvec_path = 0;  // 0 auto, 1 global-memory kernel, 2 shared-memory kernel, 3 small-k kernel,
                         // 4 small-k kernel with the carry-free radix-2^29 arithmetic,
                         // 5 tensor-core kernel (tc_kernels.cuh), 6 never the tensor-core kernel
   unsigned tc_mu = 0;   // floor(2^280 / p) when the tensor-core path serves this modulus, else 0
   unsigned* tc_error = nullptr;  // device word set by a barrier watchdog of tc_apply_kernel
   unsigned* gather_counter = nullptr;  // last-CTA detection of gather_copy_signal_kernel
+  cudaStream_t copy_streams[7] = {};   // hbg_allgather_block_ce: one stream per peer, so the copies run
+  cudaEvent_t copy_fork = nullptr, copy_join[7] = {};  // on different copy engines concurrently
   int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
   int interp_path = 0;  // fft_batch_interpolate: 0 auto, 1 V^-1 matrix, 2 NTT-structured (fnt_decode_step2)
   std::string err;
@@ -332,6 +335,7 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
 // ---------------------------------------------------------------------------
 struct TcPlan {
   unsigned ob, n_blocks, stages, ew;
+  unsigned split = 0, half = 0;  // radix-2 DFT form (tc_kernels.cuh: TcArgs::split)
   size_t b_bytes, smem;
 };
 
@@ -353,6 +357,58 @@ bool tc_plan(int n_out, int d, TcPlan* pl) {
   pl->ew = pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
   pl->smem = tc_smem_bytes(32u * d, pl->n_blocks, pl->ob, pl->stages) + 1024;
   return true;
+}
+
+// The DFT matrix (k_out x d, out[i] = sum_j in[j] w^(ij), w of order n) in the radix-2 split form:
+// `ob` pairs (i, i + n/2) per block, two half-width accumulator parts per pair.
+bool tc_plan_dft(int n, int d, int k_out, TcPlan* pl) {
+  if (n < 4 || d < 2 || d > 1024 || k_out < 1) return false;
+  const unsigned half = (unsigned)n / 2;
+  const unsigned pairs = (unsigned)k_out < half ? (unsigned)k_out : half;
+  pl->split = 1;
+  pl->half = half;
+  pl->ob = pairs < 4 ? pairs : 4;
+  pl->n_blocks = (pairs + pl->ob - 1) / pl->ob;
+  pl->b_bytes = (size_t)32 * pl->ob * 32 * d * pl->n_blocks;
+  const size_t stage = tc_stage_bytes(32u * d);
+  const size_t b_al = (pl->b_bytes + 1023) & ~(size_t)1023;
+  const size_t room = kMaxSmem - 1024;
+  if (b_al + 2 * stage > room) return false;
+  size_t st = (room - b_al) / stage;
+  pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
+  pl->ew = pl->ob == 4 ? 16 : pl->ob == 3 ? 12 : 8;
+  pl->smem = tc_smem_bytes(32u * d, pl->n_blocks, pl->ob, pl->stages) + 1024;
+  return true;
+}
+
+// Constant operand of the split form: per block, `ob` pairs; for pair i the E rows hold the bytes
+// of w^(2m i) 2^(8a) (K steps = even elements, stored first), the O rows those of
+// w^((2m+1) i) 2^(8a) (odd elements, stored after them).
+void tc_build_bmat_dft(const HostField& f, const Fe& w_mont, int d, const TcPlan& pl, std::vector<uint32_t>& host) {
+  const unsigned NB = 32 * pl.ob, K = 32u * d;
+  const unsigned n_even = ((unsigned)d + 1) / 2;
+  host.assign(pl.b_bytes / 4, 0);
+  uint8_t* b = (uint8_t*)host.data();
+  const Fe c256 = f.from_small(256);
+  const unsigned pairs = pl.ob * pl.n_blocks;
+  for (unsigned i = 0; i < pairs && i < pl.half; i++) {
+    const Fe wi = f.pow_u64(w_mont, i);
+    const unsigned nb = i / pl.ob, o = i % pl.ob;
+    Fe wij = f.one();  // w^(i j)
+    for (int j = 0; j < d; j++) {
+      const unsigned step = (j & 1) ? n_even + (unsigned)j / 2 : (unsigned)j / 2;
+      Fe cur = wij;
+      for (unsigned a = 0; a < 32; a++) {
+        const Fe s = f.from_mont(cur);
+        const uint8_t* bytes = (const uint8_t*)s.w;
+        const unsigned kb = step * 32 + a;
+        uint8_t* dst = b + (size_t)nb * NB * K + (size_t)(kb / 16) * (NB * 16) + kb % 16;
+        for (unsigned cc = 0; cc < 32; cc++) dst[(size_t)(o * 32 + cc) * 16] = bytes[cc];
+        cur = f.mul(cur, c256);
+      }
+      wij = f.mul(wij, wi);
+    }
+  }
 }
 
 bool tc_wanted(const hbg_ctx* ctx, int n_out, int d, size_t batch, TcPlan* pl) {
@@ -416,6 +472,8 @@ int launch_tc(hbg_ctx* ctx, const void* d_b, const TcPlan& pl, int n_out, int d,
   a.in_pitch = (unsigned)in_pitch;
   a.out_pitch = (unsigned)out_pitch;
   a.stages = pl.stages;
+  a.split = pl.split;
+  a.half = pl.half;
   a.mu = ctx->tc_mu;
   a.error = ctx->tc_error;
   const size_t tiles = (batch + 127) / 128;
@@ -1190,6 +1248,13 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
   if (cudaMalloc(&ctx->gather_counter, 2 * sizeof(unsigned)) != cudaSuccess ||
       cudaMemset(ctx->gather_counter, 0, 2 * sizeof(unsigned)) != cudaSuccess)
     ctx->gather_counter = nullptr;
+  if (count > 1) {  // multi-GPU box: the per-peer copy streams of hbg_allgather_block_ce
+    bool ok = cudaEventCreateWithFlags(&ctx->copy_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 7 && ok; i++)
+      ok = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ctx->copy_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) ctx->copy_fork = nullptr;
+  }
   if (ctx->is_bls) {  // the tensor-core path is instantiated for the BLS12-381 scalar field
     ctx->tc_mu = barrett_mu280(fp);
     if (cudaMalloc(&ctx->tc_error, sizeof(unsigned)) != cudaSuccess ||
@@ -1213,6 +1278,16 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->work2.p) cudaFree(ctx->work2.p);
   if (ctx->tc_error) cudaFree(ctx->tc_error);
   if (ctx->gather_counter) cudaFree(ctx->gather_counter);
+  if (ctx->copy_fork) {
+    cudaEventDestroy(ctx->copy_fork);
+    for (int i = 0; i < 7; i++) {
+      if (ctx->copy_streams[i]) {
+        cudaStreamSynchronize(ctx->copy_streams[i]);
+        cudaStreamDestroy(ctx->copy_streams[i]);
+      }
+      if (ctx->copy_join[i]) cudaEventDestroy(ctx->copy_join[i]);
+    }
+  }
   if (ctx->flags.p) cudaFree(ctx->flags.p);
   if (ctx->fnt_a.p) cudaFree(ctx->fnt_a.p);
   if (ctx->fnt_b.p) cudaFree(ctx->fnt_b.p);
@@ -1282,7 +1357,7 @@ int hbg_ctx_set_interp_path(hbg_ctx* ctx, int path) {
 }
 
 int hbg_ctx_set_fft_path(hbg_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 5) return HBG_ERR_INVALID;
+  if (!ctx || path < 0 || path > 6) return HBG_ERR_INVALID;
   ctx->fft_path = path;
   return HBG_OK;
 }
@@ -1458,11 +1533,17 @@ int hbg_allgather_block_ce(hbg_ctx* ctx, const void* block, size_t bytes, void* 
     CU(cudaGetLastError());
     ctx->launches++;
   }
+  // fork: one copy per peer, each on its own stream (= its own copy engine), then join
+  if (world > 1 && !ctx->copy_fork) return fail(ctx, HBG_ERR_CUDA, "copy streams were not created");
+  if (world > 1) CU(cudaEventRecord(ctx->copy_fork, ctx->stream));
   for (int i = 1; i < world; i++) {
     const int r = (rank + i) % world;  // staggered: at any moment the ranks target different peers
     if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
-    CU(cudaMemcpyAsync((uint8_t*)peer_out[r] + offset_bytes, block, bytes, cudaMemcpyDeviceToDevice,
-                       ctx->stream));
+    cudaStream_t cs = ctx->copy_streams[i - 1];
+    CU(cudaStreamWaitEvent(cs, ctx->copy_fork, 0));
+    CU(cudaMemcpyAsync((uint8_t*)peer_out[r] + offset_bytes, block, bytes, cudaMemcpyDeviceToDevice, cs));
+    CU(cudaEventRecord(ctx->copy_join[i - 1], cs));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_join[i - 1], 0));
   }
   gather_signal_arrived_kernel<<<1, 32, 0, ctx->stream>>>(s);
   CU(cudaGetLastError());
@@ -1584,11 +1665,26 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   double cost_ntt = (double)(n / 2) * (ilog2(n) > 1 ? ilog2(n) - 1 : 0) * 120 + 1;
   bool use_matrix = n < 2 || cost_mat <= cost_ntt;
   if (ctx->fft_path == 1 && (size_t)k_out * d_eff <= (1u << 22)) use_matrix = true;
-  if (ctx->fft_path >= 2 && n >= 2) use_matrix = false;
+  if (ctx->fft_path >= 2 && ctx->fft_path != 6 && n >= 2) use_matrix = false;
   if ((size_t)k_out * d_eff > (1u << 22)) use_matrix = false;
   // the matrix form on the tensor cores beats both whenever its constant operand fits
   TcPlan pl;
-  const bool tc = d_eff > 0 && (ctx->fft_path <= 1 || n < 2) && tc_wanted(ctx, k_out, d_eff, batch, &pl);
+  bool tc = d_eff > 0 && (ctx->fft_path <= 1 || n < 2) && tc_wanted(ctx, k_out, d_eff, batch, &pl);
+  // The radix-2 split form (half the multiply-accumulates, half the constant operand) is taken
+  // when asked for (fft path 6), or when only ITS operand fits shared memory.  It is not the
+  // default: measured, an MMA of this kernel costs about the same at N = 128 and N = 256 (operand
+  // fetch of the 128 x 32-byte A slice dominates), so halving N buys nothing and the butterfly
+  // epilogue costs a little (encode of 65 536 x 6 -> 16: 26 us split, 21 us plain).
+  const bool split_ok = d_eff > 0 && ctx->tc_mu && ctx->matvec_path != 6 &&
+                        !(ctx->matvec_path >= 1 && ctx->matvec_path <= 4);
+  if (split_ok && (ctx->fft_path == 6 || (!tc && ctx->fft_path == 0 &&
+                                          (ctx->matvec_path == 5 || batch >= kTcMinBatch)))) {
+    TcPlan sp;
+    if (tc_plan_dft(n, d_eff, k_out, &sp)) {
+      pl = sp;
+      tc = true;
+    }
+  }
   if (tc) use_matrix = true;
   const void* d_m = nullptr;
   const void* d_tw = nullptr;
@@ -1612,7 +1708,16 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
       return HBG_OK;
     };
     const std::string key = make_key("dft", omega, 32, &n, sizeof n, k_out, d_eff);
-    rc = tc ? tc_const(ctx, key, k_out, d_eff, pl, &d_m, gen)
+    rc = tc && pl.split
+             ? get_const(ctx, key + "|tcsplit", &d_m,
+                         [&](std::vector<uint32_t>& host) {
+                           Fe w;
+                           int r = check_omega(ctx, omega, n, w);
+                           if (r) return r;
+                           tc_build_bmat_dft(*ctx->field, w, d_eff, pl, host);
+                           return HBG_OK;
+                         })
+         : tc ? tc_const(ctx, key, k_out, d_eff, pl, &d_m, gen)
             : get_const(ctx, key, &d_m, [&](std::vector<uint32_t>& host) {
                 std::vector<Fe> m;
                 int r = gen(m);

@@ -52,6 +52,14 @@ struct TcArgs {
   unsigned n_blocks;         // ceil(n_out / ob)
   unsigned in_pitch, out_pitch;
   unsigned stages;           // A stages in shared memory (>= 2); one stage = ceil(K/128) boxes of 16 KB
+  // split != 0: the matrix is a DFT (out[i] = sum_j in[j] w^(ij), i < n_out <= 2*half) evaluated as
+  // one radix-2 step on top of two half-size products (the decomposition of rsdecode_impl.h:138-157
+  // by input parity): E[i] = sum_m in[2m] w^(2mi), O[i] = sum_m in[2m+1] w^((2m+1)i), i < half, and
+  // out[i] = E[i] + O[i], out[i + half] = E[i] - O[i].  A block then holds `ob` PAIRS: columns
+  // [0, 32 ob) accumulate E over the even K steps, [32 ob, 64 ob) accumulate O over the odd ones
+  // -- half the multiply-accumulates and half the constant operand of the plain form.
+  unsigned split;
+  unsigned half;             // n / 2 of the DFT (split mode)
   unsigned mu;               // floor(2^280 / p)
   // fused all-gather (hbg_fft_batch_interpolate_allgather): when gather_world > 0 the result of
   // row r is stored at row gather_row0 + r of EVERY rank's buffer -- one multimem.st per 16
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
   __shared__ unsigned tmem_base_slot;
 
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned NB = 32 * a.ob;            // accumulator columns per block
+  const unsigned NB = 32 * a.ob;            // accumulator columns per block (per part in split mode)
   const unsigned KBOX = (a.K + 127) >> 7;   // 128-byte-wide TMA boxes per tile
   const unsigned KS = a.K >> 5;             // MMA K steps (32 bytes each)
   const unsigned b_block_bytes = NB * a.K;
@@ -348,10 +356,24 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
           if (nb == 0) TC_TRACE(1, it, 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const unsigned b_base = tc_smem_u32(smem_b + (size_t)nb * b_block_bytes);
-          for (unsigned ks = 0; ks < KS && !(a.hyp & 16); ks++) {
-            const uint64_t ad = tc_smem_desc_sw128(a_base + (ks >> 2) * 16384 + (ks & 3) * 32);
-            const uint64_t bd = tc_smem_desc(b_base + ks * 2 * (NB * 16), b_lbo, b_sbo);
-            tc_mma_i8(tmem_base + buf * 256, ad, bd, idesc, ks > 0);
+          if (!a.split) {
+            for (unsigned ks = 0; ks < KS && !(a.hyp & 16); ks++) {
+              const uint64_t ad = tc_smem_desc_sw128(a_base + (ks >> 2) * 16384 + (ks & 3) * 32);
+              const uint64_t bd = tc_smem_desc(b_base + ks * 2 * (NB * 16), b_lbo, b_sbo);
+              tc_mma_i8(tmem_base + buf * 256, ad, bd, idesc, ks > 0);
+            }
+          } else {
+            // part 0 (E): even elements = even K steps; part 1 (O): odd ones.  The block's
+            // constant operand stores the even steps first, then the odd steps.
+            const unsigned n_even = (KS + 1) >> 1;
+            for (unsigned part = 0; part < 2; part++) {
+              unsigned bstep = part ? n_even : 0;
+              for (unsigned ks = part; ks < KS; ks += 2, bstep++) {
+                const uint64_t ad = tc_smem_desc_sw128(a_base + (ks >> 2) * 16384 + (ks & 3) * 32);
+                const uint64_t bd = tc_smem_desc(b_base + bstep * 2 * (NB * 16), b_lbo, b_sbo);
+                tc_mma_i8(tmem_base + buf * 256 + part * NB, ad, bd, idesc, ks > part);
+              }
+            }
           }
           tc_commit(&bar_tfull[buf]);
         }
@@ -370,6 +392,23 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
         tc_mbar_wait(&bar_tfull[buf], aph, a.error);
         if (threadIdx.x == 0 && nb == 0) TC_TRACE(2, it, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (a.split) {
+          for (unsigned o = group; o < a.ob; o += kTcEpiWarps / 4) {
+            uint32_t c[32];
+            Fe ev, od;
+            const unsigned tbase = tmem_base + ((quarter * 32) << 16) + buf * 256 + o * 32;
+            tc_ld32(tbase, c);
+            tc_fold_reduce<F>(c, a.mu, ev);
+            tc_ld32(tbase + NB, c);
+            tc_fold_reduce<F>(c, a.mu, od);
+            const unsigned i = nb * a.ob + o;
+            if (row < a.batch && i < a.half) {
+              uint8_t* orow = a.out + row * a.out_pitch;
+              if (i < a.n_out) tc_st256(orow + i * 32, fe_add<F>(ev, od));
+              if (i + a.half < a.n_out) tc_st256(orow + (i + a.half) * 32, fe_sub<F>(ev, od));
+            }
+          }
+        } else
         for (unsigned o = group; o < a.ob; o += kTcEpiWarps / 4) {
           uint32_t c[32];
           if (a.hyp & 4) continue;  // probe: no TMEM read, no arithmetic, no store

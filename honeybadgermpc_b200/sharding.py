@@ -125,13 +125,19 @@ class ShardedReconstructor:
         self.zs = np.ascontiguousarray(zs, dtype=np.int32)
         self.copy_ctas = copy_ctas
         mk_stream = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
-        self.stream, self.side, self.sync = mk_stream(), mk_stream(), mk_stream()
-        self.ctx = _native.Context(modulus, device=self.device.index)
-        self.side_ctx = _native.Context(modulus, device=self.device.index)
-        self.sync_ctx = _native.Context(modulus, device=self.device.index)
-        self.user_ctx = _native.Context(modulus, device=self.device.index)  # wait()/release() on caller streams
+        mk_ctx = lambda: _native.Context(modulus, device=self.device.index)  # noqa: E731
+        self.stream, self.sync = mk_stream(), mk_stream()
+        # one side stream per slot: the chain [wait for the release of the slot -> copies ->
+        # publish] of a step costs two engine switches (~8 us each, measured) on top of the
+        # copy itself; on separate streams the chains of consecutive steps overlap and only
+        # the copies themselves queue up on the link
+        self.sides = [mk_stream() for _ in range(depth)]
+        self.ctx, self.sync_ctx = mk_ctx(), mk_ctx()
+        self.side_ctxs = [mk_ctx() for _ in range(depth)]
+        self.user_ctx = mk_ctx()  # wait()/release() on caller streams
         self.ctx.set_stream(self.stream.cuda_stream)
-        self.side_ctx.set_stream(self.side.cuda_stream)
+        for c, st in zip(self.side_ctxs, self.sides):
+            c.set_stream(st.cuda_stream)
         self.sync_ctx.set_stream(self.sync.cuda_stream)
         self.block_bytes = self.rows * self.k * 32
         self.handles, self.gathered, self.flag_handle, self.flags = [], [], None, None
@@ -192,11 +198,12 @@ class ShardedReconstructor:
         block_row = self.rank * self.parts + part  # in units of `rows`
         if first and self.released_ev[slot] is not None:  # the local reader of the previous fill
             self.stream.wait_event(self.released_ev[slot])
+        side, side_ctx = self.sides[slot % len(self.sides)], self.side_ctxs[slot % len(self.sides)]
         if self.handles and first and not self.signal:
             # (1) everyone has released slot `slot`: its previous contents may be overwritten
-            with torch.cuda.stream(self.side):
+            with torch.cuda.stream(side):
                 self.handles[slot].barrier(channel=0)
-                self.ready_ev[slot].record(self.side)
+                self.ready_ev[slot].record(side)
             self.stream.wait_event(self.ready_ev[slot])
         elif not self.handles and first and self.pending[slot] is not None:
             self.pending[slot].wait()
@@ -215,28 +222,28 @@ class ShardedReconstructor:
                                            self.own_block_ptr(slot, part), _native.MEM_DEVICE)
         if self.handles:
             self.written_ev[slot].record(self.stream)
-            self.side.wait_event(self.written_ev[slot])
+            side.wait_event(self.written_ev[slot])
             use_mc = self.mc[slot] if self.mode.startswith("multimem") else 0
             if self.mode == "ce-copy-signal":
-                self.side_ctx.allgather_block_ce(
+                side_ctx.allgather_block_ce(
                     self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot],
                     block_row * self.block_bytes, self.rank, self.flag_peers, self.depth, slot, self.parts,
                     first)
             elif self.signal:
-                self.side_ctx.allgather_block_signal(
+                side_ctx.allgather_block_signal(
                     self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot], use_mc,
                     block_row * self.block_bytes, self.rank, self.copy_ctas, self.flag_peers, self.depth,
                     slot, self.parts, first)
             else:
-                with torch.cuda.stream(self.side):
+                with torch.cuda.stream(side):
                     if not fused:
-                        self.side_ctx.allgather_block(
+                        side_ctx.allgather_block(
                             self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot], use_mc,
                             block_row * self.block_bytes, self.copy_ctas)
                     if last:
                         # (2) every rank's blocks have landed in every buffer
                         self.handles[slot].barrier(channel=1)
-                        self.done_ev[slot].record(self.side)
+                        self.done_ev[slot].record(side)
         elif self.world > 1:
             if last:
                 with torch.cuda.stream(self.stream):
@@ -290,7 +297,8 @@ class ShardedReconstructor:
                 self.pending[slot].wait()
                 self.pending[slot] = None
         self.stream.synchronize()
-        self.side.synchronize()
+        for st in self.sides:
+            st.synchronize()
         self.sync.synchronize()
 
     # -- CUDA graph of a sequence of steps ----------------------------------------
@@ -313,7 +321,8 @@ class ShardedReconstructor:
         graph = torch.cuda.CUDAGraph()
         self.released_ev = [None] * self.depth
         with torch.cuda.graph(graph, stream=self.stream, capture_error_mode="thread_local"):
-            self.side.wait_stream(self.stream)  # fork: the side streams are part of the capture
+            for st in self.sides:  # fork: the side streams are part of the capture
+                st.wait_stream(self.stream)
             self.sync.wait_stream(self.stream)
             if begin is not None:
                 begin()
@@ -326,7 +335,8 @@ class ShardedReconstructor:
                     self.finish(slot)
             if finish is not None:
                 finish()
-            self.stream.wait_stream(self.side)
+            for st in self.sides:
+                self.stream.wait_stream(st)
             self.stream.wait_stream(self.sync)
         self.released_ev = [None] * self.depth  # events recorded inside a capture are not usable outside
         return graph

@@ -142,6 +142,11 @@ def test_fft_vs_oracle(ntl, r, d, k, batch):
     assert ntl.fft_batch_evaluate(polys, omega, P, n, k) == want
     ntl._ctx(P).set_matvec_path("tc")  # the matrix form on the tensor cores, where it fits
     assert ntl.fft_batch_evaluate(polys, omega, P, n, k) == want
+    ntl._ctx(P).set_fft_path("tc-split")  # ... and its radix-2 split form (butterfly epilogue)
+    assert ntl.fft_batch_evaluate(polys, omega, P, n, k) == want
+    if n >= 4 and 2 <= d and min(d, n) * min(k, n // 2) <= 48:
+        assert ntl._ctx(P).last_kernel() == "tc_apply_kernel"
+    ntl._ctx(P).set_fft_path("auto")
     ntl._ctx(P).set_matvec_path("auto")
 
 
