@@ -336,6 +336,7 @@ int launch_matvec(hbg_ctx* ctx, const void* mt, int n_out, int d, const void* d_
 struct TcPlan {
   unsigned ob, n_blocks, stages, ew;
   unsigned split = 0, half = 0;  // radix-2 DFT form (tc_kernels.cuh: TcArgs::split)
+  unsigned stream = 0, kpad = 0; // constant operand streamed through the stage ring (too large for smem)
   size_t b_bytes, smem;
 };
 
@@ -411,10 +412,62 @@ void tc_build_bmat_dft(const HostField& f, const Fe& w_mont, int d, const TcPlan
   }
 }
 
+// The streamed form: any n_out x d with d <= 1024 (column sums stay below 2^31).
+bool tc_plan_stream(int n_out, int d, TcPlan* pl) {
+  if (n_out < 1 || d < 1 || d > 1024) return false;
+  *pl = TcPlan();
+  pl->stream = 1;
+  pl->ob = n_out <= 8 ? (unsigned)n_out : 8u;
+  pl->n_blocks = ((unsigned)n_out + pl->ob - 1) / pl->ob;
+  pl->kpad = ((32u * d + 127) / 128) * 128;
+  pl->b_bytes = (size_t)pl->n_blocks * 32 * pl->ob * pl->kpad;
+  const size_t stage = tc_stream_stage_bytes(pl->ob);
+  size_t st = (kMaxSmem - 1024) / stage;
+  pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
+  if (pl->stages < 3) return false;
+  pl->ew = pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
+  pl->smem = (size_t)pl->stages * stage + 1024;
+  return true;
+}
+
+// Estimated cycles per SM for one 128-row tile: the streamed tensor-core form (the slower of its
+// MMA issue, ~300 cycles per 128 x N x 32 MMA measured, and its L2 -> shared-memory traffic at
+// ~20 bytes per clock per SM) against the IMAD mat-vec (64 d + 48 IMAD.WIDE per output at 31 per
+// clock per SM, ~85 % of the pipe).
+double tc_stream_tile_cycles(const TcPlan& pl, int d) {
+  const double steps = (double)pl.n_blocks * d;  // MMAs per tile (one K step = one element)
+  const double chunks = (double)pl.n_blocks * (pl.kpad / 128);
+  const double mma = steps * 300.0, l2 = chunks * (16384.0 + 32.0 * pl.ob * 128.0) / 20.0;
+  return mma > l2 ? mma : l2;
+}
+double imad_matvec_tile_cycles(int n_out, int d) { return 128.0 * n_out * (64.0 * d + 48.0) / 31.0 / 0.85; }
+
 bool tc_wanted(const hbg_ctx* ctx, int n_out, int d, size_t batch, TcPlan* pl) {
   if (!ctx->tc_mu || ctx->matvec_path == 6 || (ctx->matvec_path >= 1 && ctx->matvec_path <= 4)) return false;
-  if (!tc_plan(n_out, d, pl)) return false;
+  if (!tc_plan(n_out, d, pl)) {
+    if (!tc_plan_stream(n_out, d, pl)) return false;
+    if (ctx->matvec_path != 5 && tc_stream_tile_cycles(*pl, d) >= imad_matvec_tile_cycles(n_out, d)) return false;
+  }
   return ctx->matvec_path == 5 || batch >= kTcMinBatch;
+}
+
+// Streamed constant operand: plain row-major [n_blocks * 32 ob][kpad] bytes, row i*32 + c =
+// byte c of M[i][j] * 2^(8a) at column j*32 + a.
+void tc_build_bplain(const HostField& f, const std::vector<Fe>& m_mont, int n_out, int d, const TcPlan& pl,
+                     std::vector<uint32_t>& host) {
+  host.assign(pl.b_bytes / 4, 0);
+  uint8_t* b = (uint8_t*)host.data();
+  const Fe c256 = f.from_small(256);
+  for (int i = 0; i < n_out; i++)
+    for (int j = 0; j < d; j++) {
+      Fe cur = m_mont[(size_t)i * d + j];
+      for (unsigned a = 0; a < 32; a++) {
+        const Fe s = f.from_mont(cur);
+        const uint8_t* bytes = (const uint8_t*)s.w;
+        for (unsigned cc = 0; cc < 32; cc++) b[((size_t)i * 32 + cc) * pl.kpad + (size_t)j * 32 + a] = bytes[cc];
+        cur = f.mul(cur, c256);
+      }
+    }
 }
 
 // The constant operand of the u8 GEMM for a row-major n_out x d matrix in Montgomery form:
@@ -442,10 +495,17 @@ void tc_build_bmat(const HostField& f, const std::vector<Fe>& m_mont, int n_out,
 }
 
 template <int EW>
-int launch_tc_ew(hbg_ctx* ctx, const CUtensorMap& tm, const TcArgs& a, const TcPlan& pl, unsigned grid) {
-  int rc = allow_big_smem(ctx, tc_apply_kernel<FieldBLS, EW>);
+int launch_tc_ew(hbg_ctx* ctx, const CUtensorMap& tm, const CUtensorMap& tmb, const TcArgs& a, const TcPlan& pl,
+                 unsigned grid) {
+  if (pl.stream) {
+    int rc = allow_big_smem(ctx, tc_apply_kernel<FieldBLS, EW, true>);
+    if (rc) return rc;
+    tc_apply_kernel<FieldBLS, EW, true><<<grid, (EW + kTcLoadWarps + 1) * 32, pl.smem, ctx->stream>>>(tm, tmb, a);
+    return HBG_OK;
+  }
+  int rc = allow_big_smem(ctx, tc_apply_kernel<FieldBLS, EW, false>);
   if (rc) return rc;
-  tc_apply_kernel<FieldBLS, EW><<<grid, (EW + kTcLoadWarps + 1) * 32, pl.smem, ctx->stream>>>(tm, a);
+  tc_apply_kernel<FieldBLS, EW, false><<<grid, (EW + kTcLoadWarps + 1) * 32, pl.smem, ctx->stream>>>(tm, tmb, a);
   return HBG_OK;
 }
 
@@ -478,12 +538,15 @@ int launch_tc(hbg_ctx* ctx, const void* d_b, const TcPlan& pl, int n_out, int d,
   a.error = ctx->tc_error;
   const size_t tiles = (batch + 127) / 128;
   const unsigned grid = (unsigned)(tiles < (size_t)ctx->sm_count ? tiles : (size_t)ctx->sm_count);
-  CUtensorMap tm;
+  CUtensorMap tm, tmb;
   if (!tc_make_tmap(&tm, d_in, batch, a.K, in_pitch))
     return fail(ctx, HBG_ERR_CUDA, "cuTensorMapEncodeTiled failed (input must be 16-byte aligned)");
-  int rc = pl.ew == 16 ? launch_tc_ew<16>(ctx, tm, a, pl, grid)
-         : pl.ew == 12 ? launch_tc_ew<12>(ctx, tm, a, pl, grid)
-                       : launch_tc_ew<8>(ctx, tm, a, pl, grid);
+  tmb = tm;
+  if (pl.stream && !tc_make_tmap_b(&tmb, d_b, (unsigned long long)pl.n_blocks * 32 * pl.ob, pl.kpad, 32 * pl.ob))
+    return fail(ctx, HBG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the constant operand");
+  int rc = pl.ew == 16 ? launch_tc_ew<16>(ctx, tm, tmb, a, pl, grid)
+         : pl.ew == 12 ? launch_tc_ew<12>(ctx, tm, tmb, a, pl, grid)
+                       : launch_tc_ew<8>(ctx, tm, tmb, a, pl, grid);
   if (rc) return rc;
   CU(cudaGetLastError());
   ctx->launches++;
@@ -495,11 +558,12 @@ int launch_tc(hbg_ctx* ctx, const void* d_b, const TcPlan& pl, int n_out, int d,
 template <class Gen>
 int tc_const(hbg_ctx* ctx, const std::string& key, int n_out, int d, const TcPlan& pl, const void** d_b,
              Gen gen) {
-  return get_const(ctx, key + "|tc", d_b, [&](std::vector<uint32_t>& host) {
+  return get_const(ctx, key + (pl.stream ? "|tcs" : "|tc"), d_b, [&](std::vector<uint32_t>& host) {
     std::vector<Fe> m;
     int rc = gen(m);
     if (rc) return rc;
-    tc_build_bmat(*ctx->field, m, n_out, d, pl, host);
+    if (pl.stream) tc_build_bplain(*ctx->field, m, n_out, d, pl, host);
+    else tc_build_bmat(*ctx->field, m, n_out, d, pl, host);
     return HBG_OK;
   });
 }
@@ -1670,6 +1734,11 @@ int hbg_fft_batch_evaluate(hbg_ctx* ctx, const uint64_t omega[4], int n, const u
   // the matrix form on the tensor cores beats both whenever its constant operand fits
   TcPlan pl;
   bool tc = d_eff > 0 && (ctx->fft_path <= 1 || n < 2) && tc_wanted(ctx, k_out, d_eff, batch, &pl);
+  // a streamed operand competes with the butterflies (IMAD.WIDE at ~56 % of the pipe for the
+  // shared-memory NTT): automatic mode keeps the NTT when it is estimated faster
+  if (tc && pl.stream && ctx->fft_path == 0 && ctx->matvec_path != 5 && n >= 2 &&
+      tc_stream_tile_cycles(pl, d_eff) >= 128.0 * cost_ntt / 31.0 / 0.56)
+    tc = false;
   // The radix-2 split form (half the multiply-accumulates, half the constant operand) is taken
   // when asked for (fft path 6), or when only ITS operand fits shared memory.  It is not the
   // default: measured, an MMA of this kernel costs about the same at N = 128 and N = 256 (operand

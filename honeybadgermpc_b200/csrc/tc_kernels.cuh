@@ -256,8 +256,15 @@ HB_D void tc_st_multimem(uint8_t* p, uint32_t x, uint32_t y, uint32_t z, uint32_
     if (a.trace && blockIdx.x == 0 && (it_) < 64) a.trace[((role)*64 + (it_)) * 8 + (ev)] = clock64(); \
   } while (0)
 
-template <class F, int EW>
-__global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+// STREAM = false: the constant operand is resident in shared memory (a.bmat, canonical layout).
+// STREAM = true:  it is streamed like the input -- a.bmat is a plain row-major u8 matrix
+//   [n_blocks * 32 ob rows][ceil(K/128) * 128 bytes] described by tmap_b; a stage holds one
+//   128-byte K chunk of the input tile (16 KB) and of the current block of the operand
+//   (32 ob x 128 bytes), both 128-byte swizzled, and the K loop runs over stages.  For matrices
+//   whose operand does not fit shared memory (cfg4: 16 x 16, cfg5: 43 x 43, Gao's m x m step).
+template <class F, int EW, bool STREAM>
+__global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1)
+tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b, TcArgs a) {
   constexpr int kTcEpiWarps = EW;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_tfull[2], bar_tempty[2], bar_b;
@@ -268,8 +275,9 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
   const unsigned KBOX = (a.K + 127) >> 7;   // 128-byte-wide TMA boxes per tile
   const unsigned KS = a.K >> 5;             // MMA K steps (32 bytes each)
   const unsigned b_block_bytes = NB * a.K;
-  const unsigned b_bytes = b_block_bytes * a.n_blocks;
-  const unsigned stage_bytes = KBOX * 16384;
+  const unsigned b_bytes = STREAM ? 0u : b_block_bytes * a.n_blocks;
+  const unsigned b_chunk = NB * 128;        // STREAM: one K chunk of one block of the operand
+  const unsigned stage_bytes = STREAM ? 16384u + ((b_chunk + 1023) & ~1023u) : KBOX * 16384;
   uint8_t* smem_b = tc_smem;
   uint8_t* smem_a = tc_smem + ((b_bytes + 1023) & ~1023u);  // swizzle atoms need 1024-byte alignment
   const unsigned long long tiles = (a.batch + 127) >> 7;
@@ -287,15 +295,17 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
     tc_mbar_init(&bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    // the constant operand: one TMA bulk copy (written by the async proxy, read by the MMAs)
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&bar_b)),
-                 "r"(b_bytes)
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            tc_smem_u32(smem_b)),
-        "l"(a.bmat), "r"(b_bytes), "r"(tc_smem_u32(&bar_b))
-        : "memory");
+    if constexpr (!STREAM) {
+      // the constant operand: one TMA bulk copy (written by the async proxy, read by the MMAs)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&bar_b)),
+                   "r"(b_bytes)
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              tc_smem_u32(smem_b)),
+          "l"(a.bmat), "r"(b_bytes), "r"(tc_smem_u32(&bar_b))
+          : "memory");
+    }
   }
   if (warp == kTcEpiWarps + kTcLoadWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
@@ -313,6 +323,32 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
       unsigned it = 0;
+      if constexpr (STREAM) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+          const int row0 = (int)(tile << 7);
+          for (unsigned nb = 0; nb < a.n_blocks; nb++)
+            for (unsigned kb = 0; kb < KBOX; kb++, it++) {
+              const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
+              tc_mbar_wait(&bar_empty[s], ph ^ 1, a.error);
+              const unsigned bar = tc_smem_u32(&bar_full[s]);
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                           "r"(16384u + b_chunk)
+                           : "memory");
+              const unsigned dst = tc_smem_u32(smem_a + (size_t)s * stage_bytes);
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                  "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                  "l"(&tmap), "r"((int)(kb * 128)), "r"(row0), "r"(bar)
+                  : "memory");
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                  "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst + 16384),
+                  "l"(&tmap_b), "r"((int)(kb * 128)), "r"((int)(nb * NB)), "r"(bar)
+                  : "memory");
+            }
+        }
+      } else
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
         const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
         tc_mbar_wait(&bar_empty[s], ph ^ 1, a.error);
@@ -343,6 +379,26 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
       const unsigned idesc = (2u << 4) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
       const unsigned b_lbo = NB * 16, b_sbo = 128u;
       unsigned it = 0, acc_it = 0;
+      if constexpr (STREAM) {
+        for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+          for (unsigned nb = 0; nb < a.n_blocks; nb++, acc_it++) {
+            const unsigned buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+            tc_mbar_wait(&bar_tempty[buf], aph ^ 1, a.error);
+            for (unsigned kb = 0; kb < KBOX; kb++, it++) {
+              const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
+              tc_mbar_wait(&bar_full[s], ph, a.error);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const unsigned a_base = tc_smem_u32(smem_a + (size_t)s * stage_bytes);
+              const unsigned steps = KS - 4 * kb < 4 ? KS - 4 * kb : 4;
+              for (unsigned ks = 0; ks < steps; ks++)
+                tc_mma_i8(tmem_base + buf * 256, tc_smem_desc_sw128(a_base + ks * 32),
+                          tc_smem_desc_sw128(a_base + 16384 + ks * 32), idesc, (kb | ks) > 0);
+              tc_commit(&bar_empty[s]);
+            }
+            tc_commit(&bar_tfull[buf]);
+          }
+        }
+      } else {
       tc_mbar_wait(&bar_b, 0, a.error);
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
         const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
@@ -379,6 +435,7 @@ __global__ void __launch_bounds__((EW + kTcLoadWarps + 1) * 32, 1) tc_apply_kern
         }
         tc_commit(&bar_empty[s]);
         TC_TRACE(1, it, 2);
+      }
       }
     }
   } else {
@@ -485,6 +542,26 @@ inline bool tc_make_tmap(CUtensorMap* m, const void* in, unsigned long long batc
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+// Host: the TMA descriptor of a streamed constant operand: plain row-major u8 [rows][kpad], boxes of
+// 128 bytes x box_rows (= 32 ob) rows, 128-byte swizzle.
+inline bool tc_make_tmap_b(CUtensorMap* m, const void* bmat, unsigned long long rows, unsigned kpad,
+                           unsigned box_rows) {
+  CUtensorMap tmp;
+  if (!tc_make_tmap(&tmp, bmat, rows, kpad, kpad)) return false;  // resolves the entry point, checks alignment
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+  const cuuint64_t dims[2] = {kpad, rows};
+  const cuuint64_t strides[1] = {kpad};
+  const cuuint32_t box[2] = {128, box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  return ((tc_encode_fn)p)(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(bmat), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline size_t tc_stream_stage_bytes(unsigned ob) { return 16384 + (((size_t)32 * ob * 128 + 1023) & ~(size_t)1023); }
 
 // Host: shared memory the kernel needs for (K, n_blocks, ob, stages) -- plus up to 1008 bytes
 // the kernel may skip to align its dynamic shared memory window to 1024.

@@ -84,7 +84,8 @@ class ShardedReconstructor:
     domain.  ``depth`` gather slots rotate, so up to ``depth`` steps are in
     flight.  ``gather``:
 
-      ``"auto"``     (= ``"ce"``) the interpolation kernel writes its block into its own
+      ``"auto"``     ``"ce"`` for two ranks, ``"mc"`` from four ranks on (measured).
+      ``"ce"``       the interpolation kernel writes its block into its own
                      slot of the local gather buffer; on a side stream the COPY ENGINES
                      push it to every peer (``hbg_allgather_block_ce``: one
                      ``cudaMemcpyAsync`` per peer into the symmetric-memory mapping, no
@@ -158,7 +159,11 @@ class ShardedReconstructor:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(self.group)  # every rank's flags are zero before anyone signals
                 mc = int(getattr(self.handles[0], "multicast_ptr", 0) or 0)
-                self.mode = {"auto": "ce-copy-signal", "ce": "ce-copy-signal",
+                # measured (profiles/r2_scale_*): at 2 ranks the copy engines win (36 vs 57 us per
+                # cfg2 step), from 4 ranks on the multicast copy kernel does (83 vs 91 us at 4,
+                # 154 vs 238 us at 8: one egress copy that the switch replicates, instead of N-1)
+                auto = "ce-copy-signal" if (self.world <= 2 or not mc) else "multimem-copy-signal"
+                self.mode = {"auto": auto, "ce": "ce-copy-signal",
                              "mc": "multimem-copy-signal" if mc else "p2p-copy-signal",
                              "p2p": "p2p-copy-signal",
                              "fused": "fused-multimem" if mc else "fused-p2p",

@@ -14,6 +14,10 @@ WANT = [
     "launch__occupancy_limit_shared_mem",
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.sum", "sm__inst_executed_pipe_tensor.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_bytes.sum", "smsp__cycles_active.avg",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",

@@ -164,13 +164,13 @@ int main(int argc, char** argv) {
       printf("tensor map creation failed\n");
       exit(4);
     }
-    if (ew == 8) tc_apply_kernel<FieldBLS, 8><<<grid_, (8 + kTcLoadWarps + 1) * 32, smem>>>(tm, args);
-    else if (ew == 12) tc_apply_kernel<FieldBLS, 12><<<grid_, (12 + kTcLoadWarps + 1) * 32, smem>>>(tm, args);
-    else tc_apply_kernel<FieldBLS, 16><<<grid_, (16 + kTcLoadWarps + 1) * 32, smem>>>(tm, args);
+    if (ew == 8) tc_apply_kernel<FieldBLS, 8, false><<<grid_, (8 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
+    else if (ew == 12) tc_apply_kernel<FieldBLS, 12, false><<<grid_, (12 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
+    else tc_apply_kernel<FieldBLS, 16, false><<<grid_, (16 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
   };
-  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const size_t tiles = (batch + 127) / 128;
