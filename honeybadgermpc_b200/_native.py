@@ -93,6 +93,7 @@ SIGNATURES = {
          ctypes.c_int]),
     "hbg_ctx_set_cache_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "hbg_ctx_set_interp_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "hbg_ctx_set_wb_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_allgather_block_signal": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
@@ -285,6 +286,9 @@ class Context:
         self._check(self.lib.hbg_compare_columns(
             self.handle, int(rows_ptr), row_width, col_offset, int(colbuf_ptr), batch, _ptr(idx), len(idx),
             int(flags_dev_ptr), _ptr(flags_host)))
+
+    def set_wb_path(self, path):
+        self._check(self.lib.hbg_ctx_set_wb_path(self.handle, {"auto": 0, "exact": 1}[path]))
 
     def set_interp_path(self, path):
         self._check(self.lib.hbg_ctx_set_interp_path(self.handle, {"auto": 0, "matrix": 1, "fnt": 2}[path]))

@@ -62,7 +62,8 @@ struct hbg_ctx {
   std::string err;
   uint64_t launches = 0;
   const char* last_kernel = "";
-  DevBuf in, out, work, work2, fnt_a, fnt_b;
+  DevBuf in, out, work, work2, fnt_a, fnt_b, wbtmp, wbtmp2;
+  int wb_path = 0;      // 0: unique-decoding shortcut + exact kernel for the rest, 1: exact kernel only
   // host-buffer pipeline: H2D / D2H streams and a ring of staging slots, so that with
   // hbg_ctx_set_host_async consecutive calls overlap (call i+1's H2D under call i's D2H)
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -432,12 +433,13 @@ bool tc_plan_stream(int n_out, int d, TcPlan* pl) {
 
 // Estimated cycles per SM for one 128-row tile: the streamed tensor-core form (the slower of its
 // MMA issue, ~300 cycles per 128 x N x 32 MMA measured, and its L2 -> shared-memory traffic at
-// ~20 bytes per clock per SM) against the IMAD mat-vec (64 d + 48 IMAD.WIDE per output at 31 per
+// ~40 bytes per clock per SM: cfg5's 43 x 43 interpolation measured 0.257 ms per 131 072 rows
+// = 72k cycles per tile for 3.2 MB) against the IMAD mat-vec (64 d + 48 IMAD.WIDE per output at 31 per
 // clock per SM, ~85 % of the pipe).
 double tc_stream_tile_cycles(const TcPlan& pl, int d) {
   const double steps = (double)pl.n_blocks * d;  // MMAs per tile (one K step = one element)
   const double chunks = (double)pl.n_blocks * (pl.kpad / 128);
-  const double mma = steps * 300.0, l2 = chunks * (16384.0 + 32.0 * pl.ob * 128.0) / 20.0;
+  const double mma = steps * 300.0, l2 = chunks * (16384.0 + 32.0 * pl.ob * 128.0) / 40.0;
   return mma > l2 ? mma : l2;
 }
 double imad_matvec_tile_cycles(int n_out, int d) { return 128.0 * n_out * (64.0 * d + 48.0) / 31.0 / 0.85; }
@@ -1061,17 +1063,16 @@ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 extern "C" {
 
-int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const uint64_t* ys,
-                         size_t batch, uint64_t* coeffs, uint64_t* locator, int loc_stride,
-                         int32_t* loc_len, int32_t* status, int mem) {
-  if (!ctx) return HBG_ERR_INVALID;
-  if (m < 1 || k < 1 || !xs) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+}  // extern "C"
+
+namespace {
+
+// Gao decode of `batch` words already in device memory (all pointers device): constants for the
+// point set, the interpolants g1 by one matrix product, the EEA kernel.  Nothing is copied or
+// synchronised here.
+int gao_device(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const uint4* d_ys, size_t batch, uint4* d_co,
+               uint4* d_lo, int loc_stride, int* d_len, int* d_st) {
   const int thr = (m + k) / 2;  // rsdecode_impl.h:338
-  if (loc_stride < m - thr + 1 || loc_stride < 1)
-    return fail(ctx, HBG_ERR_INVALID, "loc_stride must be at least m - (m+k)/2 + 1");
-  if (mem != HBG_MEM_HOST && mem != HBG_MEM_DEVICE) return fail(ctx, HBG_ERR_INVALID, "bad mem flag");
-  CU(cudaSetDevice(ctx->device));
-  { int trc = cache_trim(ctx); if (trc) return trc; }
   // constants: V(x)^-1 scaled into "double Montgomery" form (so that the interpolants come
   // out of apply_matrix in Montgomery form) and g0 = prod (X - x_i)
   const void* d_m = nullptr;
@@ -1091,38 +1092,11 @@ int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const u
                  });
   if (rc) return rc;
   if (batch == 0) return HBG_OK;
-  if (!ys || !coeffs || !locator || !loc_len || !status)
-    return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
   const size_t per_warp = (size_t)8 * (m + 1) * 16;
   int warps = (int)(kMaxSmem / per_warp);
   if (warps < 1) return fail(ctx, HBG_ERR_UNSUPPORTED, "received word too long for shared memory");
   if (warps > 8) warps = 8;
-
-  const size_t ys_b = batch * (size_t)m * 32, co_b = batch * (size_t)k * 32;
-  const size_t lo_b = batch * (size_t)loc_stride * 32, i_b = align16(batch * 4);
-  const uint4* d_ys;
-  uint8_t* d_out = nullptr;
-  uint4 *d_co, *d_lo;
-  int *d_len, *d_st;
-  if (mem == HBG_MEM_HOST) {
-    rc = ensure(ctx, ctx->in, ys_b);
-    if (rc) return rc;
-    rc = ensure(ctx, ctx->out, co_b + lo_b + 2 * i_b);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->in.p, ys, ys_b, cudaMemcpyHostToDevice, ctx->stream));
-    d_ys = (const uint4*)ctx->in.p;
-    d_out = (uint8_t*)ctx->out.p;
-    d_co = (uint4*)d_out;
-    d_lo = (uint4*)(d_out + co_b);
-    d_len = (int*)(d_out + co_b + lo_b);
-    d_st = (int*)(d_out + co_b + lo_b + i_b);
-  } else {
-    d_ys = (const uint4*)ys;
-    d_co = (uint4*)coeffs;
-    d_lo = (uint4*)locator;
-    d_len = loc_len;
-    d_st = status;
-  }
+  const size_t ys_b = batch * (size_t)m * 32, lo_b = batch * (size_t)loc_stride * 32;
   rc = ensure(ctx, ctx->work, ys_b);
   if (rc) return rc;
   rc = launch_matvec(ctx, d_m, m, m, d_ys, m, ctx->work.p, m, batch);
@@ -1159,13 +1133,121 @@ int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const u
   CU(cudaGetLastError());
   ctx->launches++;
   ctx->last_kernel = "gao_kernel";
-  if (mem == HBG_MEM_HOST) {
+  return HBG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, const uint64_t* ys,
+                         size_t batch, uint64_t* coeffs, uint64_t* locator, int loc_stride,
+                         int32_t* loc_len, int32_t* status, int mem) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (m < 1 || k < 1 || !xs) return fail(ctx, HBG_ERR_INVALID, "bad size or null points");
+  const int thr = (m + k) / 2;  // rsdecode_impl.h:338
+  if (loc_stride < m - thr + 1 || loc_stride < 1)
+    return fail(ctx, HBG_ERR_INVALID, "loc_stride must be at least m - (m+k)/2 + 1");
+  if (mem != HBG_MEM_HOST && mem != HBG_MEM_DEVICE) return fail(ctx, HBG_ERR_INVALID, "bad mem flag");
+  CU(cudaSetDevice(ctx->device));
+  { int trc = cache_trim(ctx); if (trc) return trc; }
+  if (batch && (!ys || !coeffs || !locator || !loc_len || !status))
+    return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
+  const size_t ys_b = batch * (size_t)m * 32, co_b = batch * (size_t)k * 32;
+  const size_t lo_b = batch * (size_t)loc_stride * 32, i_b = align16(batch * 4);
+  const uint4* d_ys = (const uint4*)ys;
+  uint4 *d_co = (uint4*)coeffs, *d_lo = (uint4*)locator;
+  int *d_len = loc_len, *d_st = status;
+  int rc;
+  if (mem == HBG_MEM_HOST && batch) {
+    rc = ensure(ctx, ctx->in, ys_b);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->out, co_b + lo_b + 2 * i_b);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->in.p, ys, ys_b, cudaMemcpyHostToDevice, ctx->stream));
+    d_ys = (const uint4*)ctx->in.p;
+    uint8_t* d_out = (uint8_t*)ctx->out.p;
+    d_co = (uint4*)d_out;
+    d_lo = (uint4*)(d_out + co_b);
+    d_len = (int*)(d_out + co_b + lo_b);
+    d_st = (int*)(d_out + co_b + lo_b + i_b);
+  }
+  rc = gao_device(ctx, xs, m, k, d_ys, batch, d_co, d_lo, loc_stride, d_len, d_st);
+  if (rc) return rc;
+  if (mem == HBG_MEM_HOST && batch) {
     CU(cudaMemcpyAsync(coeffs, d_co, co_b, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(locator, d_lo, lo_b, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(loc_len, d_len, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(status, d_st, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  return HBG_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Exact Welch-Berlekamp elimination of `batch` words in device memory (no copies, no sync).
+int wb_device(hbg_ctx* ctx, const void* d_pw, int pw_stride, int m, int k, int e_max, const uint4* d_ys,
+              size_t batch, uint4* d_co, int* d_len, int* d_st) {
+  if (batch == 0) return HBG_OK;
+  const int nrows = m + 1, max_cols = 2 * e_max + k + 2;
+  const size_t scratch = ((size_t)2 * nrows + 2 * max_cols + 2 * m) * 16 +
+                         (size_t)((3 * max_cols + 8 + nrows + 3) & ~3) * 4;
+  const size_t mat = (size_t)2 * nrows * max_cols * 16;
+  const bool in_smem = scratch + mat <= kMaxSmem;
+  if (scratch > kMaxSmem) return fail(ctx, HBG_ERR_UNSUPPORTED, "system too large");
+  size_t blocks = batch;
+  size_t cap = (size_t)ctx->sm_count * (in_smem ? (kMaxSmem / (scratch + mat) > 8 ? 8 : kMaxSmem / (scratch + mat)) : 4);
+  if (blocks > cap) blocks = cap;
+  WbArgs a;
+  a.pw = (const uint4*)d_pw;
+  a.ys = d_ys;
+  a.coeffs = d_co;
+  a.out_len = d_len;
+  a.status = d_st;
+  a.work = nullptr;
+  a.work_stride = mat / 16;
+  a.batch = batch;
+  a.m = m;
+  a.k = k;
+  a.e_max = e_max;
+  a.pw_stride = pw_stride;
+  a.in_smem = in_smem ? 1 : 0;
+  int rc;
+  if (!in_smem) {
+    rc = ensure(ctx, ctx->work2, mat * blocks);
+    if (rc) return rc;
+    a.work = (uint4*)ctx->work2.p;
+  }
+  rc = bind_field(ctx, true);
+  if (rc) return rc;
+  // the kernel writes the coefficients of decoded words only: rows of failed words read as zero
+  CU(cudaMemsetAsync(d_co, 0, batch * (size_t)k * 32, ctx->stream));
+  size_t smem = scratch + (in_smem ? mat : 0);
+  if (ctx->is_bls) {
+    rc = allow_big_smem(ctx, wb_kernel<FieldBLS>);
+    if (rc) return rc;
+    wb_kernel<FieldBLS><<<(unsigned)blocks, kWbThreads, smem, ctx->stream>>>(a);
+  } else {
+    rc = allow_big_smem(ctx, wb_kernel<FieldAny>);
+    if (rc) return rc;
+    wb_kernel<FieldAny><<<(unsigned)blocks, kWbThreads, smem, ctx->stream>>>(a);
+  }
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "wb_kernel";
+  return HBG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbg_ctx_set_wb_path(hbg_ctx* ctx, int path) {
+  if (!ctx || path < 0 || path > 1) return HBG_ERR_INVALID;
+  ctx->wb_path = path;
   return HBG_OK;
 }
 
@@ -1197,15 +1279,6 @@ int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_ma
   if (rc) return rc;
   if (batch == 0) return HBG_OK;
   if (!ys || !coeffs || !out_len || !status) return fail(ctx, HBG_ERR_INVALID, "null batch buffer");
-  const int nrows = m + 1, max_cols = 2 * e_max + k + 2;
-  const size_t scratch = ((size_t)2 * nrows + 2 * max_cols + 2 * m) * 16 +
-                         (size_t)((3 * max_cols + 8 + nrows + 3) & ~3) * 4;
-  const size_t mat = (size_t)2 * nrows * max_cols * 16;
-  const bool in_smem = scratch + mat <= kMaxSmem;
-  if (scratch > kMaxSmem) return fail(ctx, HBG_ERR_UNSUPPORTED, "system too large");
-  size_t blocks = batch;
-  size_t cap = (size_t)ctx->sm_count * (in_smem ? (kMaxSmem / (scratch + mat) > 8 ? 8 : kMaxSmem / (scratch + mat)) : 4);
-  if (blocks > cap) blocks = cap;
 
   const size_t ys_b = batch * (size_t)m * 32, co_b = batch * (size_t)k * 32, i_b = align16(batch * 4);
   const uint4* d_ys;
@@ -1228,40 +1301,61 @@ int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_ma
     d_len = out_len;
     d_st = status;
   }
-  WbArgs a;
-  a.pw = (const uint4*)d_pw;
-  a.ys = d_ys;
-  a.coeffs = d_co;
-  a.out_len = d_len;
-  a.status = d_st;
-  a.work = nullptr;
-  a.work_stride = mat / 16;
-  a.batch = batch;
-  a.m = m;
-  a.k = k;
-  a.e_max = e_max;
-  a.pw_stride = pw_stride;
-  a.in_smem = in_smem ? 1 : 0;
-  if (!in_smem) {
-    rc = ensure(ctx, ctx->work2, mat * blocks);
+
+  // Unique-decoding shortcut.  With 2 e_max + k <= m (i.e. m - (k-1) odd, as for every n = 3t+1)
+  // the word has at most e_max errors iff the Gao decoder succeeds (same capacity), and then
+  // EVERY solution (Q, E) of the reference's e = e_max system satisfies Q = P E: Q - P E has degree
+  // < e_max + k and vanishes on the >= m - e_max >= e_max + k error-free points.  So the reference
+  // returns exactly P = the Gao result, at its first iteration (reed_solomon_wb.py:87-126).  Words the
+  // Gao kernel rejects are beyond capacity: the reference ends in one of its failure modes, which the
+  // exact elimination kernel reproduces -- it runs on those words only.
+  const bool shortcut = ctx->wb_path == 0 && 2 * e_max + k <= m && ctx->sm_count > 0;
+  if (!shortcut) {
+    rc = wb_device(ctx, d_pw, pw_stride, m, k, e_max, d_ys, batch, d_co, d_len, d_st);
     if (rc) return rc;
-    a.work = (uint4*)ctx->work2.p;
-  }
-  rc = bind_field(ctx, true);
-  if (rc) return rc;
-  size_t smem = scratch + (in_smem ? mat : 0);
-  if (ctx->is_bls) {
-    rc = allow_big_smem(ctx, wb_kernel<FieldBLS>);
-    if (rc) return rc;
-    wb_kernel<FieldBLS><<<(unsigned)blocks, kWbThreads, smem, ctx->stream>>>(a);
   } else {
-    rc = allow_big_smem(ctx, wb_kernel<FieldAny>);
+    const int loc_stride = m - (m + k) / 2 + 1;
+    const size_t lo_b = batch * (size_t)loc_stride * 32;
+    rc = ensure(ctx, ctx->wbtmp, lo_b + i_b);
     if (rc) return rc;
-    wb_kernel<FieldAny><<<(unsigned)blocks, kWbThreads, smem, ctx->stream>>>(a);
+    uint4* d_lo = (uint4*)ctx->wbtmp.p;
+    int* d_ll = (int*)((uint8_t*)ctx->wbtmp.p + lo_b);
+    rc = gao_device(ctx, xs, m, k, d_ys, batch, d_co, d_lo, loc_stride, d_ll, d_st);
+    if (rc) return rc;
+    unsigned long long blocks = (batch + 255) / 256;
+    wb_strip_kernel<<<(unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, ctx->stream>>>(d_co, d_st, d_len, batch, k);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    // which words need the exact kernel?
+    std::vector<int> st(batch);
+    CU(cudaMemcpyAsync(st.data(), d_st, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> failed;
+    for (size_t i = 0; i < batch; i++)
+      if (st[i] != 0) failed.push_back((int)i);
+    if (!failed.empty()) {
+      const size_t nf = failed.size();
+      const size_t f_ys = nf * (size_t)m * 32, f_co = nf * (size_t)k * 32, f_i = align16(nf * 4);
+      rc = ensure(ctx, ctx->wbtmp2, f_ys + f_co + 3 * f_i);
+      if (rc) return rc;
+      uint8_t* t = (uint8_t*)ctx->wbtmp2.p;
+      uint4* f_dys = (uint4*)t;
+      uint4* f_dco = (uint4*)(t + f_ys);
+      int* f_len = (int*)(t + f_ys + f_co);
+      int* f_st = (int*)(t + f_ys + f_co + f_i);
+      int* f_idx = (int*)(t + f_ys + f_co + 2 * f_i);
+      CU(cudaMemcpyAsync(f_idx, failed.data(), nf * 4, cudaMemcpyHostToDevice, ctx->stream));
+      rows_gather_kernel<<<(unsigned)((nf * m * 2 + 255) / 256), 256, 0, ctx->stream>>>(d_ys, f_dys, f_idx, nf, m * 2);
+      CU(cudaGetLastError());
+      rc = wb_device(ctx, d_pw, pw_stride, m, k, e_max, f_dys, nf, f_dco, f_len, f_st);
+      if (rc) return rc;
+      rows_scatter_kernel<<<(unsigned)((nf * k * 2 + 255) / 256), 256, 0, ctx->stream>>>(f_dco, d_co, f_idx, nf, k * 2,
+                                                                                   f_len, f_st, d_len, d_st);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(ctx->stream));  // `failed` (host) was the source of an async copy
+      ctx->launches += 2;
+    }
   }
-  CU(cudaGetLastError());
-  ctx->launches++;
-  ctx->last_kernel = "wb_kernel";
   if (mem == HBG_MEM_HOST) {
     CU(cudaMemcpyAsync(coeffs, d_co, co_b, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(out_len, d_len, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1355,6 +1449,8 @@ void hbg_ctx_destroy(hbg_ctx* ctx) {
   if (ctx->flags.p) cudaFree(ctx->flags.p);
   if (ctx->fnt_a.p) cudaFree(ctx->fnt_a.p);
   if (ctx->fnt_b.p) cudaFree(ctx->fnt_b.p);
+  if (ctx->wbtmp.p) cudaFree(ctx->wbtmp.p);
+  if (ctx->wbtmp2.p) cudaFree(ctx->wbtmp2.p);
   if (ctx->s_in) {
     cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->s_out);

@@ -457,4 +457,52 @@ __global__ void __launch_bounds__(kWbThreads) wb_kernel(WbArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// glue of the Welch-Berlekamp unique-decoding shortcut (hbg_wb_decode_batch)
+// ---------------------------------------------------------------------------
+// out_len[b] = length of coeffs[b] with trailing zeros stripped (polynomial.py:36), for the words the
+// Gao kernel decoded (status 0); the others keep status 1 until the exact kernel has seen them.
+__global__ void __launch_bounds__(256) wb_strip_kernel(const uint4* coeffs, const int* status, int* out_len,
+                                                       unsigned long long batch, int k) {
+  for (unsigned long long b = (unsigned long long)blockIdx.x * 256 + threadIdx.x; b < batch;
+       b += (unsigned long long)gridDim.x * 256) {
+    int len = 0;
+    if (status[b] == 0) {
+      for (int j = k - 1; j >= 0; j--) {
+        const uint4 lo = coeffs[2ull * (b * (unsigned)k + j)], hi = coeffs[2ull * (b * (unsigned)k + j) + 1];
+        if (lo.x | lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) {
+          len = j + 1;
+          break;
+        }
+      }
+    }
+    out_len[b] = len;
+  }
+}
+
+// dst[i] = src[idx[i]] (rows of `chunks` uint4)
+__global__ void __launch_bounds__(256) rows_gather_kernel(const uint4* src, uint4* dst, const int* idx,
+                                                          unsigned long long n, int chunks) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n * (unsigned)chunks) return;
+  const unsigned long long i = t / (unsigned)chunks;
+  const int c = (int)(t - i * (unsigned)chunks);
+  dst[t] = src[(unsigned long long)idx[i] * (unsigned)chunks + c];
+}
+
+// dst[idx[i]] = src[i], plus the per-row out_len / status
+__global__ void __launch_bounds__(256) rows_scatter_kernel(const uint4* src, uint4* dst, const int* idx,
+                                                           unsigned long long n, int chunks, const int* len_src,
+                                                           const int* st_src, int* len_dst, int* st_dst) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n * (unsigned)chunks) return;
+  const unsigned long long i = t / (unsigned)chunks;
+  const int c = (int)(t - i * (unsigned)chunks);
+  dst[(unsigned long long)idx[i] * (unsigned)chunks + c] = src[t];
+  if (c == 0) {
+    len_dst[idx[i]] = len_src[i];
+    st_dst[idx[i]] = st_src[i];
+  }
+}
+
 }  // namespace hb

@@ -211,7 +211,9 @@ int hbg_gao_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k,
  *             (the rest of the row is zero);
  *   status 1: ValueError("found no divisors!")  -> caller returns (None, None);
  *   status 2: Exception("No solution")          -> propagates in the reference;
- *   status 3: E came out as the zero polynomial (division by zero). */
+ *   status 3: E came out as the zero polynomial (division by zero).
+ * When 2 e_max + k <= m the call may synchronise the stream even for device buffers (it reads
+ * the per-word status to pick the words that need the exact elimination kernel). */
 int hbg_wb_decode_batch(hbg_ctx* ctx, const uint64_t* xs, int m, int k, int e_max,
                         const uint64_t* ys, size_t batch,
                         uint64_t* coeffs, int32_t* out_len, int32_t* status, int mem);
@@ -251,6 +253,12 @@ int hbg_compare_columns(hbg_ctx* ctx, const uint64_t* rows, int row_width, int c
                         const uint64_t* colbuf, size_t batch,
                         const int32_t* idx, int m,
                         int32_t* flags_dev, int32_t* flags_host);
+
+/* hbg_wb_decode_batch: 0 = unique-decoding shortcut (words within the decoding radius are
+ * decoded by the Gao kernel -- the reference's solver returns the same polynomial for them --
+ * and only the others run the exact elimination, which reproduces the reference's failure
+ * modes), 1 = exact elimination for every word.  Identical outputs; the tests force both. */
+int hbg_ctx_set_wb_path(hbg_ctx* ctx, int path);
 
 /* hbg_fft_batch_interpolate: 0 = automatic (the V^-1 matrix for k <= 128, the
  * NTT-structured path of fnt_decode_step2 above), 1 = matrix, 2 = NTT-structured

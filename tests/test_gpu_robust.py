@@ -210,6 +210,46 @@ def test_config3_n64_golden(rs):
         assert rs.GaoRobustDecoder(t, pt).robust_decode_batch(perm, prow) == want[:6]
 
 
+def test_wb_shortcut_equals_exact_elimination(rs):
+    """hbg_wb_decode_batch: the unique-decoding shortcut (Gao kernel for the words within the
+    decoding radius, exact elimination kernel for the rest) returns exactly what the exact
+    kernel returns for every word -- decodable, beyond capacity (all three failure modes),
+    all-zero -- with and without erasures (the shortcut only applies when 2 e_max + k <= m)."""
+    from honeybadgermpc_b200 import robust
+    from honeybadgermpc_b200.ntl import pack_rows, pack_vec
+
+    rng = random.Random(99)
+    for p in (P, 257):
+        ctx = robust._ctx(p)
+        for n, t in ((4, 1), (7, 2), (10, 3), (16, 5), (13, 4)):
+            k = t + 1
+            for erased in (0, 1, 2):
+                m = n - erased
+                if 2 * t + 1 + erased > n:
+                    continue
+                e_max = (m - t) // 2
+                if e_max < 1:
+                    continue
+                xs = [i + 1 for i in range(n)][:m]
+                words = []
+                for w in range(60):
+                    msg = [rng.randrange(p) for _ in range(k)] if w % 7 else [0] * k
+                    word = [orc.poly_eval(msg, x, p) for x in xs]
+                    for i in rng.sample(range(m), rng.randint(0, min(m, e_max + 2))):
+                        word[i] = rng.randrange(p)
+                    words.append(word)
+                xl, yl = pack_vec(xs, p), pack_rows(words, m, p)
+                ctx.set_wb_path("exact")
+                want = robust.wb_decode_batch_limbs(xl, yl, k, e_max, p)
+                assert ctx.last_kernel() == "wb_kernel"
+                ctx.set_wb_path("auto")
+                got = robust.wb_decode_batch_limbs(xl, yl, k, e_max, p)
+                for a, b in zip(got, want):
+                    assert np.array_equal(a, b), (p, n, t, erased)
+                assert set(want[2].tolist()) <= {0, 1, 2, 3}
+        ctx.set_wb_path("auto")
+
+
 def test_gao_equals_wb_when_decodable(rs):
     rng = random.Random(8)
     n, t = 16, 5

@@ -85,6 +85,19 @@ def main():
         ms_enc = timed(lambda: ctx.fft_batch_evaluate(omega, pt.order, c.data_ptr(), batch, k, n, e.data_ptr(),
                                                       _native.MEM_DEVICE), 5, stream)
         k_enc = ctx.last_kernel()
+        enc_variants = {}
+        for name, fft_path, mv_path in (("ntt_smem_kernel (IMAD butterflies)", "ntt", "auto"),
+                                        ("tc_apply_kernel, streamed 128x43 DFT matrix", "matrix", "tc")):
+            ctx.set_fft_path(fft_path)
+            ctx.set_matvec_path(mv_path)
+            e2 = torch.empty_like(e)
+            enc_variants[name] = timed(lambda: ctx.fft_batch_evaluate(omega, pt.order, c.data_ptr(), batch, k, n,
+                                                                      e2.data_ptr(), _native.MEM_DEVICE), 5, stream)
+            stream.synchronize()
+            assert torch.equal(e2, e), name
+            del e2
+        ctx.set_fft_path("auto")
+        ctx.set_matvec_path("auto")
         zs = sorted(random.Random(5).sample(range(n), k))
         y = e.index_select(1, torch.tensor(zs, device="cuda")).contiguous()
         r = torch.empty((batch, k, 4), dtype=torch.int64, device="cuda")
@@ -95,6 +108,7 @@ def main():
         assert torch.equal(r, c), "cfg5 round trip"
         out.append({"config": f"cfg5 shard n=128 t=42 batch={batch} (1/8 of 1 Mi)", "encode_kernel": k_enc,
                     "interpolate_kernel": k_dec, "encode_ms": ms_enc, "interpolate_ms": ms_dec,
+                    "encode_ms_by_kernel": enc_variants,
                     "shares_per_s": batch * k / ((ms_enc + ms_dec) * 1e-3),
                     "GBps_algorithmic": batch * (3 * k + n) * E / ((ms_enc + ms_dec) * 1e-3) / 1e9})
 
