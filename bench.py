@@ -199,7 +199,7 @@ def run_cfg5(args, world, rank, local, dev):
     pt = EvalPoint(GF(P), n, True)
     omega = pack_vec([pt.omega.value], P)[0]
     zs = sorted(random.Random(5).sample(range(n), k))
-    gather = "auto" if args.gather == "fused" else args.gather  # k = 43: no fused epilogue
+    gather = "auto" if args.gather.startswith("fused") else args.gather  # k = 43: no fused epilogue
     rec = ShardedReconstructor(P, omega, pt.order, zs, piece, device=local, depth=2, gather=gather,
                                copy_ctas=args.gather_ctas, parts=parts)
     ctx, stream = rec.ctx, rec.stream
@@ -357,6 +357,13 @@ def run_b200(args):
     ctx_enc.set_stream(enc_stream.cuda_stream)
     if args.matvec_path != "auto":
         ctx_enc.set_matvec_path(args.matvec_path)
+    sm_split = None
+    if overlap_encode and args.sm_split > 0:
+        # the two kernels side by side on disjoint SMs instead of one after the other
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_split = [min(args.sm_split, n_sm - 1), n_sm - min(args.sm_split, n_sm - 1)]
+        ctx_enc.set_sm_limit(sm_split[0])
+        ctx.set_sm_limit(sm_split[1])
 
     def encode(s):
         ctx_enc.fft_batch_evaluate(omega, pt.order, c_ptr[s], batch, K, N_PARTIES, e_ptr[s], _native.MEM_DEVICE)
@@ -407,7 +414,8 @@ def run_b200(args):
                 print(f"[bench] CUDA graph capture failed ({exc!r}); eager step loop", file=sys.stderr)
             graph = None
             barrier()
-    launches_per_step = 2 + (3 if rec.signal else 1 if rec.mode.endswith("copy") else 0)
+    launches_per_step = 2 + ((4 if rec.mode in ("ce-copy-signal",) or rec.mode.startswith("fused") else 3)
+                             if rec.signal else 1 if rec.mode.endswith("copy") else 0)
 
     def run_steps(n_steps):
         """enqueue n_steps (a multiple of `unit` when the graph is used)"""
@@ -532,6 +540,33 @@ def run_b200(args):
                                    "by HBM / the TMEM-read epilogue, not by the MMA rate"},
                 "note": "256-bit modular arithmetic as an integer GEMM whose constant operand absorbs "
                         "the reduction (DESIGN.md section 4)"}
+    # ---- the write side of the roofline, measured live: a pure write stream (memset) reaches only
+    # about half of the copy bandwidth on this part, and 65 % of a step's traffic is writes (the
+    # encode: 73 %), so max(bytes / copy peak, written bytes / write peak) is the tighter floor
+    wbuf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        wbuf.zero_()
+        w0.record(stream)
+        for _ in range(5):
+            wbuf.zero_()
+        w1.record(stream)
+    stream.synchronize()
+    write_peak = 5 * wbuf.numel() / (w0.elapsed_time(w1) * 1e-3) / 1e9
+    del wbuf
+    written = {"encode": batch * N_PARTIES * E, "interpolate": batch * K * E}
+    step_written = written["encode"] + written["interpolate"] + (nb_link if world > 1 else 0)
+    floor_ms = {k: max(written[k] / write_peak, b / peak) / 1e6
+                for k, b in (("encode", enc_bytes), ("interpolate", dec_bytes))}
+    step_floor_ms = max(step_written / write_peak, (enc_bytes + dec_bytes + (2 * nb_link if world > 1 else 0)) / peak) / 1e6
+    roofline["hbm_write"] = {
+        "write_peak_GBps": write_peak, "how": "5 x memset of 1 GiB on the bench stream, CUDA events",
+        "written_bytes_per_launch": written[dom], "kernel_floor_ms": floor_ms[dom],
+        "kernel_frac_of_floor": floor_ms[dom] / dom_ms,
+        "step_written_bytes": step_written, "step_floor_ms": step_floor_ms,
+        "step_frac_of_floor": step_floor_ms / ms_per_step,
+        "note": "floor = max(all bytes / copy peak, written bytes / write peak); `frac` above keeps the "
+                "contract's definition (algorithmic bytes / copy peak)"}
     if world > 1:
         link = 770.0  # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
         roofline["nvlink"] = {"ingress_bytes_per_step": nb_link, "link_GBps": link,
@@ -623,6 +658,8 @@ def run_b200(args):
                              "(inputs+outputs larger than the 126 MB L2)",
                        "streams": ("encode and interpolate of a step on two streams" if overlap_encode
                                    else "one stream"),
+                       "sm_split": ({"encode": sm_split[0], "interpolate": sm_split[1]} if sm_split
+                                    else "every launch may use all SMs"),
                        "step_loop": (f"CUDA graph of {unit} steps, replayed" if graph is not None
                                      else "eager Python loop"),
                        "parallelism": f"batch shard x{world}" + (f" + all-gather ({rec.mode})" if world > 1 else ""),
@@ -654,7 +691,7 @@ def main():
                     help="with overlapped streams: record per-kernel events on every n-th step only")
     ap.add_argument("--serial", action="store_true",
                     help="N=1: run the two kernels of a step back to back on one stream")
-    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "mc", "p2p", "fused", "copy", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "mc", "p2p", "fused", "fused-barrier", "copy", "nccl"],
                     help="N>1: auto = ce = local store + copy-engine peer copies on a side stream, slot hand-over "
                          "by device flags; mc = multimem.st copy kernel + flags; p2p = peer-store copy kernel "
                          "+ flags; "
@@ -668,6 +705,9 @@ def main():
     ap.add_argument("--cfg5-passes", type=int, default=5)
     ap.add_argument("--min-ms", type=float, default=60.0,
                     help="the timed region is extended (more steps) until it lasts at least this long")
+    ap.add_argument("--sm-split", type=int, default=0,
+                    help="CTAs (SMs) of the encode launches; the interpolation gets the rest, so that the two "
+                         "persistent kernels of a step run side by side (0 = both use every SM, back to back)")
     ap.add_argument("--graph-units", type=int, default=4,
                     help="steps per captured graph = lcm(sets, slots) x this (a replay ends with a join of "
                          "all streams, i.e. drains the gather pipeline once)")

@@ -92,6 +92,8 @@ SIGNATURES = {
          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
          ctypes.c_int]),
     "hbg_ctx_set_cache_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "hbg_ctx_set_sm_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "hbg_ctx_set_tc_store": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_ctx_set_interp_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_ctx_set_wb_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_allgather_block_signal": (
@@ -107,6 +109,10 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
          ctypes.c_int]),
+    "hbg_gather_fence": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int]),
     "hbg_gather_release": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
@@ -271,6 +277,14 @@ class Context:
     def set_cache_limit(self, nbytes):
         self._check(self.lib.hbg_ctx_set_cache_limit(self.handle, int(nbytes)))
 
+    def set_tc_store(self, mode):
+        """"staged" (default: through shared memory, full 128-byte lines) or "direct" (32 bytes per thread)"""
+        self._check(self.lib.hbg_ctx_set_tc_store(self.handle, {"staged": 0, "direct": 1}[mode]))
+
+    def set_sm_limit(self, ctas):
+        """At most `ctas` CTAs (= SMs) per tensor-core launch of this context; 0 = all."""
+        self._check(self.lib.hbg_ctx_set_sm_limit(self.handle, int(ctas)))
+
     def columns_to_rows(self, colbuf_ptr, batch, idx, rows_ptr):
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         self._check(self.lib.hbg_columns_to_rows(self.handle, int(colbuf_ptr), batch, _ptr(idx), len(idx),
@@ -308,6 +322,12 @@ class Context:
 
     def gather_wait(self, flags_arr, rank, n_slots, slot, parts):
         self._check(self.lib.hbg_gather_wait(self.handle, flags_arr, len(flags_arr), rank, n_slots, slot, parts))
+
+    def gather_fence(self, flags_arr, rank, n_slots, slot, parts, phase):
+        """phase 0: wait until every rank has released the slot; phase 1: signal that this rank's
+        part has landed everywhere (around a fill the caller does itself: the fused gather)"""
+        self._check(self.lib.hbg_gather_fence(self.handle, flags_arr, len(flags_arr), rank, n_slots, slot, parts,
+                                              phase))
 
     def gather_release(self, flags_arr, rank, n_slots, slot):
         self._check(self.lib.hbg_gather_release(self.handle, flags_arr, len(flags_arr), rank, n_slots, slot))

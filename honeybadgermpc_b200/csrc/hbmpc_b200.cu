@@ -75,6 +75,8 @@ struct hbg_ctx {
   unsigned next_slot = 0;
   bool host_async = false;
   int sm_count = 148;
+  int sm_limit = 0;     // tensor-core launches use at most this many CTAs (0 = sm_count)
+  int tc_store = 0;     // tensor-core epilogue: 0 staged full-line stores when possible, 1 per-thread stores
   std::unordered_map<std::string, DevConst> cache;
   std::unordered_map<std::string, std::vector<uint32_t>> host_cache;  // small tables passed by value
   size_t cache_bytes = 0;
@@ -338,6 +340,7 @@ struct TcPlan {
   unsigned ob, n_blocks, stages, ew;
   unsigned split = 0, half = 0;  // radix-2 DFT form (tc_kernels.cuh: TcArgs::split)
   unsigned stream = 0, kpad = 0; // constant operand streamed through the stage ring (too large for smem)
+  unsigned staged = 0;           // results leave through shared-memory staging, full-line stores (EW = 16)
   size_t b_bytes, smem;
 };
 
@@ -352,12 +355,15 @@ bool tc_plan(int n_out, int d, TcPlan* pl) {
   pl->b_bytes = (size_t)32 * pl->ob * 32 * d * pl->n_blocks;
   const size_t stage = tc_stage_bytes(32u * d);
   const size_t b_al = (pl->b_bytes + 1023) & ~(size_t)1023;
-  const size_t room = kMaxSmem - 1024;  // the kernel may skip up to 1008 bytes to align its window
+  size_t room = kMaxSmem - 1024;  // the kernel may skip up to 1008 bytes to align its window
   if (b_al + 2 * stage > room) return false;  // >= 2 stages: one tile in flight behind the MMA
+  // staged, full-line stores whenever their 32 KB leave room for the stages
+  pl->staged = b_al + 2 * stage + kTcStoreStaging <= room ? 1u : 0u;
+  if (pl->staged) room -= kTcStoreStaging;
   size_t st = (room - b_al) / stage;
   pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
-  pl->ew = pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
-  pl->smem = tc_smem_bytes(32u * d, pl->n_blocks, pl->ob, pl->stages) + 1024;
+  pl->ew = pl->staged || pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
+  pl->smem = tc_smem_bytes(32u * d, pl->n_blocks, pl->ob, pl->stages) + 1024 + (pl->staged ? kTcStoreStaging : 0);
   return true;
 }
 
@@ -423,11 +429,12 @@ bool tc_plan_stream(int n_out, int d, TcPlan* pl) {
   pl->kpad = ((32u * d + 127) / 128) * 128;
   pl->b_bytes = (size_t)pl->n_blocks * 32 * pl->ob * pl->kpad;
   const size_t stage = tc_stream_stage_bytes(pl->ob);
-  size_t st = (kMaxSmem - 1024) / stage;
+  size_t st = (kMaxSmem - 1024 - kTcStoreStaging) / stage;
   pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
   if (pl->stages < 3) return false;
-  pl->ew = pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
-  pl->smem = (size_t)pl->stages * stage + 1024;
+  pl->staged = 1;
+  pl->ew = 16;
+  pl->smem = (size_t)pl->stages * stage + 1024 + kTcStoreStaging;
   return true;
 }
 
@@ -539,13 +546,24 @@ int launch_tc(hbg_ctx* ctx, const void* d_b, const TcPlan& pl, int n_out, int d,
   a.mu = ctx->tc_mu;
   a.error = ctx->tc_error;
   const size_t tiles = (batch + 127) / 128;
-  const unsigned grid = (unsigned)(tiles < (size_t)ctx->sm_count ? tiles : (size_t)ctx->sm_count);
+  const size_t ctas = ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count;
+  const unsigned grid = (unsigned)(tiles < ctas ? tiles : ctas);
   CUtensorMap tm, tmb;
   if (!tc_make_tmap(&tm, d_in, batch, a.K, in_pitch))
     return fail(ctx, HBG_ERR_CUDA, "cuTensorMapEncodeTiled failed (input must be 16-byte aligned)");
   tmb = tm;
   if (pl.stream && !tc_make_tmap_b(&tmb, d_b, (unsigned long long)pl.n_blocks * 32 * pl.ob, pl.kpad, 32 * pl.ob))
     return fail(ctx, HBG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the constant operand");
+  // staged stores write 16 bytes per thread: they need 16-byte aligned destinations; otherwise the
+  // epilogue stores 32 bytes per thread
+  a.staged = pl.staged && ctx->tc_store != 1 && pl.ew == 16 && !(out_pitch & 15);
+  if (gather) {
+    if ((uintptr_t)gather->mc & 15) a.staged = 0;
+    for (int r = 0; r < gather->world; r++)
+      if ((uintptr_t)gather->peers[r] & 15) a.staged = 0;
+  } else if ((uintptr_t)d_out & 15) {
+    a.staged = 0;
+  }
   int rc = pl.ew == 16 ? launch_tc_ew<16>(ctx, tm, tmb, a, pl, grid)
          : pl.ew == 12 ? launch_tc_ew<12>(ctx, tm, tmb, a, pl, grid)
                        : launch_tc_ew<8>(ctx, tm, tmb, a, pl, grid);
@@ -1510,6 +1528,12 @@ int hbg_ctx_set_matvec_path(hbg_ctx* ctx, int path) {
   return HBG_OK;
 }
 
+int hbg_ctx_set_tc_store(hbg_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return HBG_ERR_INVALID;
+  ctx->tc_store = mode;
+  return HBG_OK;
+}
+
 int hbg_ctx_set_interp_path(hbg_ctx* ctx, int path) {
   if (!ctx || path < 0 || path > 2) return HBG_ERR_INVALID;
   ctx->interp_path = path;
@@ -1709,6 +1733,23 @@ int hbg_allgather_block_ce(hbg_ctx* ctx, const void* block, size_t bytes, void* 
   CU(cudaGetLastError());
   ctx->launches++;
   ctx->last_kernel = "gather_signal_arrived_kernel";
+  return HBG_OK;
+}
+
+int hbg_gather_fence(hbg_ctx* ctx, void* const* flags_peers, int world, int rank, int n_slots, int slot,
+                     int parts, int phase) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (phase != 0 && phase != 1) return fail(ctx, HBG_ERR_INVALID, "phase is 0 (before the fill) or 1 (after it)");
+  CU(cudaSetDevice(ctx->device));
+  GatherSignal s;
+  int rc = gather_signal(ctx, flags_peers, world, rank, n_slots, slot, parts, &s);
+  if (rc) return rc;
+  if (phase == 0)
+    gather_wait_released_kernel<<<1, 32, 0, ctx->stream>>>(s);
+  else
+    gather_signal_arrived_kernel<<<1, 32, 0, ctx->stream>>>(s);
+  CU(cudaGetLastError());
+  ctx->launches++;
   return HBG_OK;
 }
 
@@ -1970,6 +2011,13 @@ int hbg_fft_batch_interpolate(hbg_ctx* ctx, const uint64_t omega[4], int n, cons
 int hbg_ctx_set_cache_limit(hbg_ctx* ctx, size_t bytes) {
   if (!ctx) return HBG_ERR_INVALID;
   ctx->cache_limit = bytes;
+  return HBG_OK;
+}
+
+int hbg_ctx_set_sm_limit(hbg_ctx* ctx, int ctas) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (ctas < 0) return fail(ctx, HBG_ERR_INVALID, "sm limit must be >= 0");
+  ctx->sm_limit = ctas;
   return HBG_OK;
 }
 

@@ -97,8 +97,10 @@ class ShardedReconstructor:
                      switch replicates it; ``hbg_allgather_block_signal``)
       ``"p2p"``      the copy kernel with peer stores only
       ``"fused"``    the kernel epilogue stores into every rank's buffer itself
-                     (``hbg_fft_batch_interpolate_allgather``), hand-over by two
-                     symmetric-memory barriers per step on the side stream
+                     (``hbg_fft_batch_interpolate_allgather``: full 128-byte lines through
+                     the multicast address or to every peer, no second pass over the block),
+                     hand-over by the same device flags (``hbg_gather_fence``)
+      ``"fused-barrier"``  the same with two symmetric-memory barriers per step (round 1)
       ``"copy"``     copy kernel + the two barriers (round 1's protocol)
       ``"nccl"``     local store + ``all_gather_into_tensor`` on NCCL's stream
 
@@ -166,7 +168,8 @@ class ShardedReconstructor:
                 self.mode = {"auto": auto, "ce": "ce-copy-signal",
                              "mc": "multimem-copy-signal" if mc else "p2p-copy-signal",
                              "p2p": "p2p-copy-signal",
-                             "fused": "fused-multimem" if mc else "fused-p2p",
+                             "fused": "fused-multimem-signal" if mc else "fused-p2p-signal",
+                             "fused-barrier": "fused-multimem" if mc else "fused-p2p",
                              "copy": "multimem-copy" if mc else "p2p-copy"}[gather]
             except Exception as exc:  # noqa: BLE001 - no symmetric memory on this build / fabric
                 self.fallback_reason = repr(exc)
@@ -219,9 +222,13 @@ class ShardedReconstructor:
             base = (block_row - self.rank) * self.block_bytes
             peers = self.peers[slot] if base == 0 else _native.Context.peer_array(
                 [int(p) + base for p in self.handles[slot].buffer_ptrs])
-            mc = self.mc[slot] + base if (self.mode == "fused-multimem") else 0
+            mc = self.mc[slot] + base if self.mode.startswith("fused-multimem") else 0
+            if self.signal and first:  # every rank has released the slot
+                self.ctx.gather_fence(self.flag_peers, self.rank, self.depth, slot, self.parts, 0)
             self.ctx.fft_batch_interpolate_allgather(self.omega, self.order, self.zs, y_ptr, self.rows,
                                                      peers, mc, self.rank)
+            if self.signal:            # this rank's part has landed in every buffer
+                self.ctx.gather_fence(self.flag_peers, self.rank, self.depth, slot, self.parts, 1)
         else:
             self.ctx.fft_batch_interpolate(self.omega, self.order, self.zs, y_ptr, self.rows,
                                            self.own_block_ptr(slot, part), _native.MEM_DEVICE)
@@ -229,7 +236,9 @@ class ShardedReconstructor:
             self.written_ev[slot].record(self.stream)
             side.wait_event(self.written_ev[slot])
             use_mc = self.mc[slot] if self.mode.startswith("multimem") else 0
-            if self.mode == "ce-copy-signal":
+            if fused and self.signal:
+                pass  # the kernel stored into every buffer and the fences above did the hand-over
+            elif self.mode == "ce-copy-signal":
                 side_ctx.allgather_block_ce(
                     self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot],
                     block_row * self.block_bytes, self.rank, self.flag_peers, self.depth, slot, self.parts,

@@ -157,6 +157,14 @@ int hbg_allgather_block(hbg_ctx* ctx, const void* block, size_t bytes,
                         void* const* peer_out, void* multicast_out,
                         size_t offset_bytes, int world, int max_ctas);
 
+/* The two halves of the hand-over around a fill of slot `slot` that the caller does itself (the
+ * fused hbg_fft_batch_interpolate_allgather, whose epilogue stores into every rank's buffer):
+ * phase 0, before the first part -- the stream waits until every rank has released the slot;
+ * phase 1, after each part -- tells every rank that this rank's part has landed.  Same flag
+ * protocol as hbg_allgather_block_signal / _ce, stream-ordered and CUDA-graph capturable. */
+int hbg_gather_fence(hbg_ctx* ctx, void* const* flags_peers, int world, int rank, int n_slots, int slot,
+                     int parts, int phase);
+
 /* hbg_allgather_block with the slot hand-over on the device (no host-issued barrier).
  * flags_peers[r] is rank r's flag array (uint32, symmetric memory, zero-initialised, at
  * least n_slots * (2 * world + 2) entries) as mapped into this process.  Per slot it holds
@@ -269,6 +277,18 @@ int hbg_ctx_set_interp_path(hbg_ctx* ctx, int path);
 /* Test hook: bound (bytes) of the per-context cache of device constants; when it
  * is exceeded the cache is dropped at the entry of the next call (default 256 MB). */
 int hbg_ctx_set_cache_limit(hbg_ctx* ctx, size_t bytes);
+
+/* How the tensor-core kernel writes its results: 0 = transposed through shared memory so that
+ * every store instruction writes full 128-byte lines (whenever the output is 16-byte aligned),
+ * 1 = one 32-byte store per thread.  Identical bits; the tests force both. */
+int hbg_ctx_set_tc_store(hbg_ctx* ctx, int mode);
+
+/* Upper bound on the CTAs (one per SM) a persistent tensor-core launch of this context uses;
+ * 0 = all SMs (default).  A tensor-core CTA owns its SM's shared memory, so two launches of
+ * 148 CTAs on two streams run one after the other; two contexts whose limits add up to the SM
+ * count run side by side (the NTL reference has no counterpart: it is single-threaded per
+ * call, and SetNumThreads, pyx:321, is the nearest knob). */
+int hbg_ctx_set_sm_limit(hbg_ctx* ctx, int ctas);
 
 #ifdef __cplusplus
 }

@@ -172,6 +172,15 @@ def test_tensor_core_path(ntl):
                 ctx.set_matvec_path("tc")
                 got = ntl.vandermonde_batch_evaluate(xs, polys, P)
                 assert ctx.last_kernel() == "tc_apply_kernel", (n, d)
+                # the two store paths of the epilogue (staged full-line stores / 32 bytes per thread)
+                # and a launch confined to a few CTAs (hbg_ctx_set_sm_limit)
+                ctx.set_tc_store("direct")
+                ctx.set_sm_limit(3)
+                try:
+                    assert got == ntl.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch, "direct stores")
+                finally:
+                    ctx.set_tc_store("staged")
+                    ctx.set_sm_limit(0)
                 ctx.set_matvec_path("no-tc")
                 assert got == ntl.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch)
                 assert ctx.last_kernel() != "tc_apply_kernel"

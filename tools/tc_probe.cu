@@ -40,6 +40,7 @@ int main(int argc, char** argv) {
   const unsigned stages = argc > 7 ? atoi(argv[7]) : 4;
   const int reps = argc > 8 ? atoi(argv[8]) : 20;
   const int ew = argc > 9 ? atoi(argv[9]) : 12;
+  const int staged = argc > 10 ? atoi(argv[10]) : (ew == 16);  // staged full-line stores (EW = 16 only)
 
   FieldParams fp;
   if (!field_params_init(kBlsP, &fp)) return 1;
@@ -156,7 +157,8 @@ int main(int argc, char** argv) {
   a.hyp = hyp;
   a.debug = d_dbg;
   a.error = d_err;
-  const size_t smem = tc_smem_bytes(K, n_blocks, ob, stages);
+  a.staged = staged && ew == 16;
+  const size_t smem = tc_smem_bytes(K, n_blocks, ob, stages) + (a.staged ? kTcStoreStaging : 0);
   printf("smem %zu bytes\n", smem);
   auto launch = [&](const TcArgs& args, unsigned grid_) {
     CUtensorMap tm;
@@ -164,13 +166,13 @@ int main(int argc, char** argv) {
       printf("tensor map creation failed\n");
       exit(4);
     }
-    if (ew == 8) tc_apply_kernel<FieldBLS, 8, false><<<grid_, (8 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
-    else if (ew == 12) tc_apply_kernel<FieldBLS, 12, false><<<grid_, (12 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
-    else tc_apply_kernel<FieldBLS, 16, false><<<grid_, (16 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
+    if (ew == 8) tc_apply_kernel<FieldBLS, 8, false, true><<<grid_, (8 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
+    else if (ew == 12) tc_apply_kernel<FieldBLS, 12, false, true><<<grid_, (12 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
+    else tc_apply_kernel<FieldBLS, 16, false, true><<<grid_, (16 + kTcLoadWarps + 1) * 32, smem>>>(tm, tm, args);
   };
-  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 12, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tc_apply_kernel<FieldBLS, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const size_t tiles = (batch + 127) / 128;
@@ -202,7 +204,14 @@ int main(int argc, char** argv) {
     }
     printf("raw accumulators (first tile): %s (%zu mismatches)\n", bad ? "FAIL" : "ok", bad);
   }
-  // full outputs vs the host field code (sampled rows)
+  // full outputs vs the host field code (sampled rows), from a launch without the debug dump
+  // (= the production epilogue)
+  if (!(hyp & ~0u)) {
+    a.debug = nullptr;
+    CK(cudaMemset(d_out, 0xAB, out_bytes));
+    launch(a, grid);
+    CK(cudaDeviceSynchronize());
+  }
   {
     std::vector<Fe> out((size_t)batch * n_out);
     CK(cudaMemcpy(out.data(), d_out, out_bytes, cudaMemcpyDeviceToHost));
@@ -237,14 +246,14 @@ int main(int argc, char** argv) {
     a.trace = nullptr;
     const long long t0 = tr[(0 * 64 + 0) * 8 + 0];
     if (getenv("TC_TRACE")) {
-      printf("tile | loader: empty issued landed arrived | mma: full tempty committed | epi: tfull done arrived\n");
+      printf("tile | loader: empty issued | mma: full tempty0 released tempty1 issued0 issued1 | epi(warp 0): tfull0 done0 arrived0 tfull1 done1 arrived1\n");
       for (int t = 0; t < 24; t++) {
         printf("%3d |", t);
-        for (int e = 0; e < 4; e++) printf(" %7lld", tr[(0 * 64 + t) * 8 + e] ? tr[(0 * 64 + t) * 8 + e] - t0 : 0);
+        for (int e = 0; e < 2; e++) printf(" %7lld", tr[(0 * 64 + t) * 8 + e] ? tr[(0 * 64 + t) * 8 + e] - t0 : 0);
         printf(" |");
-        for (int e = 0; e < 3; e++) printf(" %7lld", tr[(1 * 64 + t) * 8 + e] ? tr[(1 * 64 + t) * 8 + e] - t0 : 0);
+        for (int e = 0; e < 6; e++) printf(" %7lld", tr[(1 * 64 + t) * 8 + e] ? tr[(1 * 64 + t) * 8 + e] - t0 : 0);
         printf(" |");
-        for (int e = 0; e < 3; e++) printf(" %7lld", tr[(2 * 64 + t) * 8 + e] ? tr[(2 * 64 + t) * 8 + e] - t0 : 0);
+        for (int e = 0; e < 6; e++) printf(" %7lld", tr[(2 * 64 + t) * 8 + e] ? tr[(2 * 64 + t) * 8 + e] - t0 : 0);
         printf("\n");
       }
     }
