@@ -206,6 +206,8 @@ def run_cfg5(args, world, rank, local, dev):
     enc_stream = torch.cuda.Stream(device=dev)
     ctx_enc = _native.Context(P, device=local)
     ctx_enc.set_stream(enc_stream.cuda_stream)
+    if rec.compute_sms > 0:
+        ctx_enc.set_sm_limit(rec.compute_sms)
     rng = np.random.default_rng(0xB205 + rank)
     zs_t = torch.tensor(zs, device=dev)
     with torch.cuda.stream(stream):
@@ -316,7 +318,7 @@ def run_b200(args):
     # the sharded reconstructor owns the interpolation context / stream and the gather slots
     depth = sets if world == 1 else min(3, sets)
     rec = ShardedReconstructor(P, omega, pt.order, ZS, batch, device=local, depth=depth,
-                               gather=args.gather, copy_ctas=args.gather_ctas)
+                               gather=args.gather, copy_ctas=args.gather_ctas, compute_sms=args.sm_limit)
     ctx, stream = rec.ctx, rec.stream
     if args.matvec_path != "auto":
         ctx.set_matvec_path(args.matvec_path)
@@ -357,6 +359,8 @@ def run_b200(args):
     ctx_enc.set_stream(enc_stream.cuda_stream)
     if args.matvec_path != "auto":
         ctx_enc.set_matvec_path(args.matvec_path)
+    if rec.compute_sms > 0:  # --sm-limit, or the reconstructor's own choice (copy kernel on its own SMs)
+        ctx_enc.set_sm_limit(rec.compute_sms)
     sm_split = None
     if overlap_encode and args.sm_split > 0:
         # the two kernels side by side on disjoint SMs instead of one after the other
@@ -659,6 +663,7 @@ def run_b200(args):
                        "streams": ("encode and interpolate of a step on two streams" if overlap_encode
                                    else "one stream"),
                        "sm_split": ({"encode": sm_split[0], "interpolate": sm_split[1]} if sm_split
+                                    else f"every launch may use {rec.compute_sms} SMs" if rec.compute_sms
                                     else "every launch may use all SMs"),
                        "step_loop": (f"CUDA graph of {unit} steps, replayed" if graph is not None
                                      else "eager Python loop"),
@@ -691,7 +696,7 @@ def main():
                     help="with overlapped streams: record per-kernel events on every n-th step only")
     ap.add_argument("--serial", action="store_true",
                     help="N=1: run the two kernels of a step back to back on one stream")
-    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "mc", "p2p", "fused", "fused-barrier", "copy", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "mc", "p2p", "bulk", "fused", "fused-barrier", "copy", "nccl"],
                     help="N>1: auto = ce = local store + copy-engine peer copies on a side stream, slot hand-over "
                          "by device flags; mc = multimem.st copy kernel + flags; p2p = peer-store copy kernel "
                          "+ flags; "
@@ -705,6 +710,9 @@ def main():
     ap.add_argument("--cfg5-passes", type=int, default=5)
     ap.add_argument("--min-ms", type=float, default=60.0,
                     help="the timed region is extended (more steps) until it lasts at least this long")
+    ap.add_argument("--sm-limit", type=int, default=0,
+                    help="SMs the encode and the interpolation launches may use (0 = all): the rest stay free "
+                         "for the gather's copy kernel (N > 1)")
     ap.add_argument("--sm-split", type=int, default=0,
                     help="CTAs (SMs) of the encode launches; the interpolation gets the rest, so that the two "
                          "persistent kernels of a step run side by side (0 = both use every SM, back to back)")

@@ -105,6 +105,10 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
          ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hbg_allgather_block_bulk": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hbg_gather_wait": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -319,6 +323,12 @@ class Context:
         self._check(self.lib.hbg_allgather_block_ce(
             self.handle, int(block_ptr), nbytes, peer_arr, offset_bytes, len(peer_arr), rank, flags_arr,
             n_slots, slot, parts, 1 if first_part else 0))
+
+    def allgather_block_bulk(self, block_ptr, nbytes, peer_arr, offset_bytes, rank, max_ctas, flags_arr, n_slots,
+                             slot, parts, first_part):
+        self._check(self.lib.hbg_allgather_block_bulk(
+            self.handle, int(block_ptr), nbytes, peer_arr, offset_bytes, len(peer_arr), rank, max_ctas,
+            flags_arr, n_slots, slot, parts, 1 if first_part else 0))
 
     def gather_wait(self, flags_arr, rank, n_slots, slot, parts):
         self._check(self.lib.hbg_gather_wait(self.handle, flags_arr, len(flags_arr), rank, n_slots, slot, parts))

@@ -1702,6 +1702,38 @@ int hbg_allgather_block_signal(hbg_ctx* ctx, const void* block, size_t bytes, vo
   return HBG_OK;
 }
 
+int hbg_allgather_block_bulk(hbg_ctx* ctx, const void* block, size_t bytes, void* const* peer_out,
+                             size_t offset_bytes, int world, int rank, int max_ctas, void* const* flags_peers,
+                             int n_slots, int slot, int parts, int first_part) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (!block || !peer_out || world < 1 || world > 8 || (bytes & 15) || (offset_bytes & 15) || bytes == 0 ||
+      ((uintptr_t)block & 15))
+    return fail(ctx, HBG_ERR_INVALID, "bad argument (pointers, sizes and offsets must be non-zero multiples of 16)");
+  CU(cudaSetDevice(ctx->device));
+  GatherSignal s;
+  int rc = gather_signal(ctx, flags_peers, world, rank, n_slots, slot, parts, &s);
+  if (rc) return rc;
+  s.first_part = first_part;
+  GatherDst g;
+  memset(&g, 0, sizeof(g));
+  g.world = world;
+  for (int r = 0; r < world; r++) {
+    if (!peer_out[r] || ((uintptr_t)peer_out[r] & 15)) return fail(ctx, HBG_ERR_INVALID, "null or unaligned peer pointer");
+    g.peers[r] = (uint4*)peer_out[r];
+  }
+  const size_t smem = (size_t)kGbStages * kGbChunk;
+  rc = allow_big_smem(ctx, gather_bulk_signal_kernel);
+  if (rc) return rc;
+  unsigned long long want = (bytes + kGbChunk - 1) / kGbChunk;
+  unsigned ctas = (unsigned)(max_ctas > 0 ? max_ctas : 16);
+  if (ctas > want) ctas = (unsigned)want;
+  gather_bulk_signal_kernel<<<ctas, 64, smem, ctx->stream>>>((const uint8_t*)block, g, offset_bytes, bytes, s);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_kernel = "gather_bulk_signal_kernel";
+  return HBG_OK;
+}
+
 int hbg_allgather_block_ce(hbg_ctx* ctx, const void* block, size_t bytes, void* const* peer_out,
                            size_t offset_bytes, int world, int rank, void* const* flags_peers, int n_slots,
                            int slot, int parts, int first_part) {

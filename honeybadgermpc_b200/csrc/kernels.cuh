@@ -375,6 +375,109 @@ __global__ void __launch_bounds__(256) gather_copy_signal_kernel(const uint4* sr
   }
 }
 
+// The same hand-over around a copy done by the TMA unit: per CTA one thread streams 16 KB chunks of the
+// local block into a ring of shared-memory stages (cp.async.bulk global -> shared) and another
+// thread forwards every chunk to each PEER's buffer (cp.async.bulk shared -> global over NVLink),
+// so a handful of SMs keeps megabytes in flight without occupying registers or load/store slots.
+// Unicast only (bulk copies do not take multicast addresses): egress = (world - 1) blocks, ingress =
+// (world - 1) blocks -- the multicast kernel above sends 1 block but receives world blocks (its own
+// comes back through the switch), which is the larger of the two floors from 4 ranks on.
+constexpr unsigned kGbStages = 4, kGbChunk = 16384;
+
+__global__ void __launch_bounds__(64) gather_bulk_signal_kernel(const uint8_t* src, GatherDst g,
+                                                                unsigned long long offset_bytes,
+                                                                unsigned long long bytes, GatherSignal s) {
+  extern __shared__ __align__(128) uint8_t gb_smem[];
+  __shared__ uint64_t gb_full[kGbStages], gb_empty[kGbStages];
+  unsigned* local = s.flags[s.rank];
+  const unsigned sent = ld_acquire_sys(local + s.local_base);
+  if (threadIdx.x == 0) {
+    for (unsigned i = 0; i < kGbStages; i++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&gb_full[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&gb_empty[i])));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (s.first_part && threadIdx.x < (unsigned)s.world)
+    spin_until(local + s.slot_base + s.world + threadIdx.x, sent / s.parts, s.error);
+  __syncthreads();
+  const unsigned long long n_chunks = (bytes + kGbChunk - 1) / kGbChunk;
+  auto wait = [&](uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned done;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(a), "r"(parity)
+          : "memory");
+      if (done) return;
+      if (clock64() - t0 > 4000000000ll) {
+        if (s.error) atomicExch(s.error, 3u);
+        __trap();
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    // loader
+    unsigned it = 0;
+    for (unsigned long long i = blockIdx.x; i < n_chunks; i += gridDim.x, it++) {
+      const unsigned st = it % kGbStages, ph = (it / kGbStages) & 1;
+      wait(&gb_empty[st], ph ^ 1);
+      const unsigned long long o = i * kGbChunk;
+      const unsigned size = (unsigned)(bytes - o < kGbChunk ? bytes - o : kGbChunk);
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&gb_full[st]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(size) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              (unsigned)__cvta_generic_to_shared(gb_smem + st * kGbChunk)),
+          "l"(src + o), "r"(size), "r"(bar)
+          : "memory");
+    }
+  } else if (threadIdx.x == 32) {
+    // forwarder
+    unsigned it = 0;
+    for (unsigned long long i = blockIdx.x; i < n_chunks; i += gridDim.x, it++) {
+      const unsigned st = it % kGbStages, ph = (it / kGbStages) & 1;
+      wait(&gb_full[st], ph);
+      const unsigned long long o = i * kGbChunk;
+      const unsigned size = (unsigned)(bytes - o < kGbChunk ? bytes - o : kGbChunk);
+      const unsigned sm = (unsigned)__cvta_generic_to_shared(gb_smem + st * kGbChunk);
+      for (int k = 1; k < g.world; k++) {
+        const int w = (s.rank + k) % g.world;  // staggered: the ranks target different peers at any moment
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                         (uint8_t*)g.peers[w] + offset_bytes + o),
+                     "r"(sm), "r"(size)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (it > 0) {  // the previous chunk's copies have finished reading their stage
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(&gb_empty[(it - 1) % kGbStages]))
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every copy has been performed
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 32) {
+    const unsigned done = atomicAdd(s.counter, 1u);
+    if (done == gridDim.x - 1) {  // every CTA's copies are complete and fenced: publish
+      *s.counter = 0;
+      st_release_sys(local + s.local_base, sent + 1);
+      __threadfence_system();
+      for (int w = 0; w < s.world; w++) st_release_sys(s.flags[w] + s.slot_base + s.rank, sent + 1);
+    }
+  }
+}
+
 // The hand-over around a copy done by the copy engines (cudaMemcpyAsync to the peers'
 // buffers, stream-ordered between these two one-warp kernels):
 // before -- first part of a fill: wait until every rank has released the previous fill

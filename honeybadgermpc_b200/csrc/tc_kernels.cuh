@@ -80,6 +80,7 @@ struct TcArgs {
 };
 
 constexpr int kTcMaxStages = 6;
+constexpr int kTcBBars = 4;      // the resident operand arrives in up to 4 pieces (block 0, 1, 2, the rest)
 constexpr int kTcLoadWarps = 1;  // one elected thread issues the TMA tensor copies
 
 HB_D unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -343,7 +344,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const unsigned hyp = PROBE ? a.hyp : 0u;
   uint32_t* const debug = PROBE ? a.debug : nullptr;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  __shared__ uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_tfull[2], bar_tempty[2], bar_b;
+  __shared__ uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_tfull[2], bar_tempty[2], bar_b[kTcBBars];
   __shared__ unsigned tmem_base_slot;
 
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,20 +370,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       tc_mbar_init(&bar_tfull[i], 1);
       tc_mbar_init(&bar_tempty[i], kTcEpiWarps);
     }
-    tc_mbar_init(&bar_b, 1);
+    for (int i = 0; i < kTcBBars; i++) tc_mbar_init(&bar_b[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if constexpr (!STREAM) {
-      // the constant operand: one TMA bulk copy (written by the async proxy, read by the MMAs)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&bar_b)),
-                   "r"(b_bytes)
-                   : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              tc_smem_u32(smem_b)),
-          "l"(a.bmat), "r"(b_bytes), "r"(tc_smem_u32(&bar_b))
-          : "memory");
-    }
   }
   if (warp == kTcEpiWarps + kTcLoadWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
@@ -400,6 +390,27 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
       unsigned it = 0;
+      // The resident constant operand: one TMA bulk copy per piece (block 0, 1, 2, the rest), each on
+      // its own barrier, queued BEHIND the first input tile -- the MMAs of block 0 start once that
+      // tile and a 1 / n_blocks share of the operand are in, not after all of it (98 KB per CTA for
+      // the cfg2 encode: most of the kernel's fill time).
+      auto issue_b = [&]() {
+        for (unsigned g = 0; g < (unsigned)kTcBBars; g++) {
+          const unsigned first = g, count = g + 1 < (unsigned)kTcBBars ? 1u : (a.n_blocks > g ? a.n_blocks - g : 0u);
+          const unsigned bytes = first < a.n_blocks ? b_block_bytes * count : 0u;
+          const unsigned bar = tc_smem_u32(&bar_b[g]);
+          if (bytes == 0) {
+            tc_mbar_arrive(&bar_b[g]);
+            continue;
+          }
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  tc_smem_u32(smem_b + (size_t)first * b_block_bytes)),
+              "l"(a.bmat + (size_t)first * b_block_bytes), "r"(bytes), "r"(bar)
+              : "memory");
+        }
+      };
       if constexpr (STREAM) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -425,13 +436,17 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                   : "memory");
             }
         }
-      } else
+      } else {
+#ifdef TC_B_FIRST  // A/B experiment: the operand ahead of the first tile
+      issue_b();
+#endif
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
         const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
         tc_mbar_wait(&bar_empty[s], ph ^ 1, a.error);
         TC_TRACE(0, it, 0);
         const unsigned bar = tc_smem_u32(&bar_full[s]);
         if (hyp & 8) {  // probe: no loads
+          if (it == 0) issue_b();
           tc_mbar_arrive(&bar_full[s]);
           continue;
         }
@@ -445,7 +460,11 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst + kb * 16384),
               "l"(&tmap), "r"((int)(kb * 128)), "r"(row0), "r"(bar)
               : "memory");
+#ifndef TC_B_FIRST
+        if (it == 0) issue_b();
+#endif
         TC_TRACE(0, it, 1);
+      }
       }
     }
   } else if (warp == kTcEpiWarps + kTcLoadWarps) {
@@ -482,7 +501,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           }
         }
       } else {
-      tc_mbar_wait(&bar_b, 0, a.error);
       const unsigned b_step = (2 * (NB * 16)) >> 4;  // descriptor units (16 bytes) per K step of the operand
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
         const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
@@ -496,6 +514,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           tc_mbar_wait(&bar_tempty[buf], aph ^ 1, a.error);
           if (lane == 0 && nb < 2) TC_TRACE(1, it, 1 + 2 * nb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (it == 0) tc_mbar_wait(&bar_b[nb < (unsigned)kTcBBars ? nb : kTcBBars - 1], 0, a.error);
           const unsigned b_base = tc_smem_u32(smem_b + (size_t)nb * b_block_bytes);
           const uint64_t bd0 = tc_smem_desc(b_base, b_lbo, b_sbo);
           const unsigned d0 = tmem_base + buf * 256;
@@ -620,17 +639,24 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&bar_tempty[buf]);
             if (threadIdx.x == 0 && nb < 2) TC_TRACE(2, it, 3 * nb + 2);
-            auto wave_body = [&](const uint32_t* c, bool has, unsigned j) {
+            // both folds first, in one straight line of code: two independent carry-chain streams
+            // for the scheduler to interleave (the epilogue is latency-bound: ~100 instructions per
+            // output at an IPC of ~0.5 per sub-partition); then the two store waves
+            Fe r0, r1;
+            auto fold = [&](const uint32_t* c, Fe& r) {
+              if (PROBE && (hyp & 128)) {  // probe: no arithmetic
+#pragma unroll
+                for (int i = 0; i < 8; i++) r.w[i] = c[i] ^ c[i + 8] ^ c[i + 16] ^ c[i + 24];
+              } else if (narrow)
+                tc_fold_reduce<F, true>(c, a.mu, r);
+              else
+                tc_fold_reduce<F, false>(c, a.mu, r);
+            };
+            if (has0) fold(c0, r0);
+            if (has1) fold(c1, r1);
+            auto wave_body = [&](const Fe& r, bool has, unsigned j) {
               const unsigned stg = stg_base + (wave & 1) * 16384;
               if (has) {
-                Fe r;
-                if (PROBE && (hyp & 128)) {  // probe: no arithmetic
-#pragma unroll
-                  for (int i = 0; i < 8; i++) r.w[i] = c[i] ^ c[i + 8] ^ c[i + 16] ^ c[i + 24];
-                } else if (narrow)
-                  tc_fold_reduce<F, true>(c, a.mu, r);
-                else
-                  tc_fold_reduce<F, false>(c, a.mu, r);
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + st_w0), "r"(r.w[0]), "r"(r.w[1]),
                              "r"(r.w[2]), "r"(r.w[3])
                              : "memory");
@@ -661,8 +687,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               }
               wave++;
             };
-            wave_body(c0, has0, 0);
-            if (n_waves > 1) wave_body(c1, has1, 1);
+            wave_body(r0, has0, 0);
+            if (n_waves > 1) wave_body(r1, has1, 1);
             if (threadIdx.x == 0 && nb < 2) TC_TRACE(2, it, 3 * nb + 1);
           }
         }

@@ -96,6 +96,9 @@ class ShardedReconstructor:
                      address (``multimem.st``: the block leaves this GPU once and the
                      switch replicates it; ``hbg_allgather_block_signal``)
       ``"p2p"``      the copy kernel with peer stores only
+      ``"bulk"``     a copy kernel that moves the block with TMA bulk copies (global -> shared ->
+                     every peer; ``hbg_allgather_block_bulk``): unicast like ``"ce"``, one launch
+                     like ``"mc"``, a few SMs
       ``"fused"``    the kernel epilogue stores into every rank's buffer itself
                      (``hbg_fft_batch_interpolate_allgather``: full 128-byte lines through
                      the multicast address or to every peer, no second pass over the block),
@@ -116,7 +119,7 @@ class ShardedReconstructor:
     strong-scaling job where the whole batch is one result (BASELINE configs[4])."""
 
     def __init__(self, modulus, omega, order, zs, rows, group=None, device=None, depth=3, gather="auto",
-                 copy_ctas=64, parts=1):
+                 copy_ctas=64, parts=1, compute_sms=0):
         import numpy as np
 
         self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
@@ -138,6 +141,11 @@ class ShardedReconstructor:
         self.ctx, self.sync_ctx = mk_ctx(), mk_ctx()
         self.side_ctxs = [mk_ctx() for _ in range(depth)]
         self.user_ctx = mk_ctx()  # wait()/release() on caller streams
+        # compute_sms > 0: the interpolation uses at most that many SMs (hbg_ctx_set_sm_limit), so
+        # the copy kernel of the gather finds free SMs instead of queueing behind a full-GPU launch
+        self.compute_sms = int(compute_sms)
+        if self.compute_sms > 0:
+            self.ctx.set_sm_limit(self.compute_sms)
         self.ctx.set_stream(self.stream.cuda_stream)
         for c, st in zip(self.side_ctxs, self.sides):
             c.set_stream(st.cuda_stream)
@@ -161,13 +169,22 @@ class ShardedReconstructor:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(self.group)  # every rank's flags are zero before anyone signals
                 mc = int(getattr(self.handles[0], "multicast_ptr", 0) or 0)
-                # measured (profiles/r2_scale_*): at 2 ranks the copy engines win (36 vs 57 us per
-                # cfg2 step), from 4 ranks on the multicast copy kernel does (83 vs 91 us at 4,
-                # 154 vs 238 us at 8: one egress copy that the switch replicates, instead of N-1)
-                auto = "ce-copy-signal" if (self.world <= 2 or not mc) else "multimem-copy-signal"
+                # measured (profiles/r2_scale_*, r2_gather_modes_n4): at 2 ranks the copy engines win
+                # (36 vs 57 us per cfg2 step); at 3-4 ranks the unicast TMA copy kernel on 16 SMs the
+                # compute kernels leave free (72 us at 4 ranks, multicast kernel 83, copy engines 95:
+                # unicast receives world-1 blocks, a multicast store world -- the sender's own block
+                # comes back through the switch); from 5 ranks on the multicast kernel (154 us at 8,
+                # copy engines 238: one block leaves the GPU instead of seven)
+                if self.world <= 2 or not mc:
+                    auto = "ce-copy-signal"
+                elif self.world <= 4:
+                    auto = "bulk-copy-signal"
+                else:
+                    auto = "multimem-copy-signal"
                 self.mode = {"auto": auto, "ce": "ce-copy-signal",
                              "mc": "multimem-copy-signal" if mc else "p2p-copy-signal",
                              "p2p": "p2p-copy-signal",
+                             "bulk": "bulk-copy-signal",
                              "fused": "fused-multimem-signal" if mc else "fused-p2p-signal",
                              "fused-barrier": "fused-multimem" if mc else "fused-p2p",
                              "copy": "multimem-copy" if mc else "p2p-copy"}[gather]
@@ -179,6 +196,14 @@ class ShardedReconstructor:
             self.gathered = [torch.empty(shape, dtype=torch.int64, device=self.device) for _ in range(depth)]
         self.depth = len(self.gathered)
         self.signal = self.mode.endswith("signal")
+        if self.mode == "bulk-copy-signal" and gather == "auto":
+            # two working threads per CTA: 16 CTAs saturate the links; the compute kernels leave
+            # them their SMs (persistent tensor-core CTAs own a whole SM each)
+            self.copy_ctas = min(self.copy_ctas, 16)
+            if self.compute_sms == 0:
+                sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+                self.compute_sms = sms - self.copy_ctas
+                self.ctx.set_sm_limit(self.compute_sms)
         self.peers = [_native.Context.peer_array(list(h.buffer_ptrs)) for h in self.handles]
         self.mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
         self.flag_peers = _native.Context.peer_array(list(self.flag_handle.buffer_ptrs)) \
@@ -238,6 +263,11 @@ class ShardedReconstructor:
             use_mc = self.mc[slot] if self.mode.startswith("multimem") else 0
             if fused and self.signal:
                 pass  # the kernel stored into every buffer and the fences above did the hand-over
+            elif self.mode == "bulk-copy-signal":
+                side_ctx.allgather_block_bulk(
+                    self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot],
+                    block_row * self.block_bytes, self.rank, self.copy_ctas, self.flag_peers, self.depth, slot,
+                    self.parts, first)
             elif self.mode == "ce-copy-signal":
                 side_ctx.allgather_block_ce(
                     self.own_block_ptr(slot, part), self.block_bytes, self.peers[slot],

@@ -185,6 +185,16 @@ int hbg_allgather_block_signal(hbg_ctx* ctx, const void* block, size_t bytes,
                                int parts, int first_part);
 int hbg_gather_wait(hbg_ctx* ctx, void* const* flags_peers, int world, int rank,
                     int n_slots, int slot, int parts);
+/* The same copy by the TMA unit: max_ctas CTAs of two working threads each stream the block
+ * through shared memory (cp.async.bulk global -> shared -> every peer's buffer), so a few SMs keep
+ * the NVLink ports busy.  Unicast like the copy engines (world-1 copies leave this GPU, world-1
+ * arrive: the lower of the two ingress floors from 4 ranks on -- a multicast store also delivers
+ * the sender's own block back to it), a kernel like hbg_allgather_block_signal (one launch, the
+ * hand-over inside it). */
+int hbg_allgather_block_bulk(hbg_ctx* ctx, const void* block, size_t bytes,
+                             void* const* peer_out, size_t offset_bytes, int world, int rank,
+                             int max_ctas, void* const* flags_peers, int n_slots, int slot,
+                             int parts, int first_part);
 /* The same copy on the COPY ENGINES (no SM touches the payload): when first_part != 0 a
  * one-warp kernel first waits for the release of the slot's previous fill; then one
  * cudaMemcpyAsync per peer (peer_out[r] + offset_bytes <- block; the local buffer already

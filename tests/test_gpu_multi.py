@@ -55,11 +55,11 @@ def _rank_main(rank, world, port, results):
                 assert np.array_equal(enc[:64][:, zs, :], ys[s][:64])  # kernels agree with the oracle
                 ys[s] = enc[:, zs, :]
             y_dev = torch.from_numpy(ys.view(np.int64)).to(dev)
-            modes = (["auto", "ce", "mc", "p2p", "fused", "fused-barrier", "copy", "nccl"] if k <= 8
-                     else ["auto", "mc", "copy", "nccl"])
+            modes = (["auto", "ce", "mc", "p2p", "bulk", "fused", "fused-barrier", "copy", "nccl"] if k <= 8
+                     else ["auto", "mc", "bulk", "copy", "nccl"])
             for gather in modes:
                 for graph in (False, True):
-                    if graph and gather not in ("auto", "ce", "mc", "p2p", "fused"):
+                    if graph and gather not in ("auto", "ce", "mc", "p2p", "bulk", "fused"):
                         continue  # CUDA graphs: the device-flag hand-over (no host-issued collective)
                     rec = ShardedReconstructor(P, omega, pt.order, zs, rows, device=rank, depth=2,
                                                gather=gather, parts=parts)
