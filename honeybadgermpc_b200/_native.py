@@ -282,8 +282,8 @@ class Context:
         self._check(self.lib.hbg_ctx_set_cache_limit(self.handle, int(nbytes)))
 
     def set_tc_store(self, mode):
-        """"staged" (default: through shared memory, full 128-byte lines) or "direct" (32 bytes per thread)"""
-        self._check(self.lib.hbg_ctx_set_tc_store(self.handle, {"staged": 0, "direct": 1}[mode]))
+        """"direct" (default: 32 bytes per thread) or "staged" (through shared memory, full 128-byte lines)"""
+        self._check(self.lib.hbg_ctx_set_tc_store(self.handle, {"direct": 0, "staged": 1}[mode]))
 
     def set_sm_limit(self, ctas):
         """At most `ctas` CTAs (= SMs) per tensor-core launch of this context; 0 = all."""

@@ -76,7 +76,7 @@ struct hbg_ctx {
   bool host_async = false;
   int sm_count = 148;
   int sm_limit = 0;     // tensor-core launches use at most this many CTAs (0 = sm_count)
-  int tc_store = 0;     // tensor-core epilogue: 0 staged full-line stores when possible, 1 per-thread stores
+  int tc_store = 0;     // tensor-core epilogue: 0 = 32-byte store per thread, 1 = staged full-line stores (opt-in)
   std::unordered_map<std::string, DevConst> cache;
   std::unordered_map<std::string, std::vector<uint32_t>> host_cache;  // small tables passed by value
   size_t cache_bytes = 0;
@@ -348,7 +348,7 @@ const size_t kTcMinBatch = 512;  // below this the IMAD kernels' latency wins (a
 
 // Shape check: the constant operand (32 n_out x 32 d bytes) stays resident in shared
 // memory next to >= 3 stages of 128-row input tiles.
-bool tc_plan(int n_out, int d, TcPlan* pl) {
+bool tc_plan(int n_out, int d, TcPlan* pl, bool want_staged = false) {
   if (n_out < 1 || d < 1 || d > 1024) return false;
   pl->ob = n_out <= 8 ? (unsigned)n_out : 8u;
   pl->n_blocks = ((unsigned)n_out + pl->ob - 1) / pl->ob;
@@ -357,8 +357,9 @@ bool tc_plan(int n_out, int d, TcPlan* pl) {
   const size_t b_al = (pl->b_bytes + 1023) & ~(size_t)1023;
   size_t room = kMaxSmem - 1024;  // the kernel may skip up to 1008 bytes to align its window
   if (b_al + 2 * stage > room) return false;  // >= 2 stages: one tile in flight behind the MMA
-  // staged, full-line stores whenever their 32 KB leave room for the stages
-  pl->staged = b_al + 2 * stage + kTcStoreStaging <= room ? 1u : 0u;
+  // staged, full-line stores (opt-in: measured slower than the per-thread stores)
+  // if their 32 KB leave room for the stages
+  pl->staged = want_staged && b_al + 2 * stage + kTcStoreStaging <= room ? 1u : 0u;
   if (pl->staged) room -= kTcStoreStaging;
   size_t st = (room - b_al) / stage;
   pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
@@ -420,7 +421,7 @@ void tc_build_bmat_dft(const HostField& f, const Fe& w_mont, int d, const TcPlan
 }
 
 // The streamed form: any n_out x d with d <= 1024 (column sums stay below 2^31).
-bool tc_plan_stream(int n_out, int d, TcPlan* pl) {
+bool tc_plan_stream(int n_out, int d, TcPlan* pl, bool want_staged = false) {
   if (n_out < 1 || d < 1 || d > 1024) return false;
   *pl = TcPlan();
   pl->stream = 1;
@@ -429,12 +430,13 @@ bool tc_plan_stream(int n_out, int d, TcPlan* pl) {
   pl->kpad = ((32u * d + 127) / 128) * 128;
   pl->b_bytes = (size_t)pl->n_blocks * 32 * pl->ob * pl->kpad;
   const size_t stage = tc_stream_stage_bytes(pl->ob);
-  size_t st = (kMaxSmem - 1024 - kTcStoreStaging) / stage;
+  const size_t staging = want_staged ? kTcStoreStaging : 0;
+  size_t st = (kMaxSmem - 1024 - staging) / stage;
   pl->stages = (unsigned)(st > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : st);
   if (pl->stages < 3) return false;
-  pl->staged = 1;
-  pl->ew = 16;
-  pl->smem = (size_t)pl->stages * stage + 1024 + kTcStoreStaging;
+  pl->staged = want_staged ? 1u : 0u;
+  pl->ew = pl->staged || pl->ob % 4 == 0 ? 16 : pl->ob % 3 == 0 ? 12 : 8;
+  pl->smem = (size_t)pl->stages * stage + 1024 + staging;
   return true;
 }
 
@@ -453,8 +455,8 @@ double imad_matvec_tile_cycles(int n_out, int d) { return 128.0 * n_out * (64.0 
 
 bool tc_wanted(const hbg_ctx* ctx, int n_out, int d, size_t batch, TcPlan* pl) {
   if (!ctx->tc_mu || ctx->matvec_path == 6 || (ctx->matvec_path >= 1 && ctx->matvec_path <= 4)) return false;
-  if (!tc_plan(n_out, d, pl)) {
-    if (!tc_plan_stream(n_out, d, pl)) return false;
+  if (!tc_plan(n_out, d, pl, ctx->tc_store == 1)) {
+    if (!tc_plan_stream(n_out, d, pl, ctx->tc_store == 1)) return false;
     if (ctx->matvec_path != 5 && tc_stream_tile_cycles(*pl, d) >= imad_matvec_tile_cycles(n_out, d)) return false;
   }
   return ctx->matvec_path == 5 || batch >= kTcMinBatch;
@@ -554,9 +556,8 @@ int launch_tc(hbg_ctx* ctx, const void* d_b, const TcPlan& pl, int n_out, int d,
   tmb = tm;
   if (pl.stream && !tc_make_tmap_b(&tmb, d_b, (unsigned long long)pl.n_blocks * 32 * pl.ob, pl.kpad, 32 * pl.ob))
     return fail(ctx, HBG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the constant operand");
-  // staged stores write 16 bytes per thread: they need 16-byte aligned destinations; otherwise the
-  // epilogue stores 32 bytes per thread
-  a.staged = pl.staged && ctx->tc_store != 1 && pl.ew == 16 && !(out_pitch & 15);
+  // the opt-in staged stores write 16 bytes per thread and need 16-byte aligned destinations
+  a.staged = pl.staged && ctx->tc_store == 1 && pl.ew == 16 && !(out_pitch & 15);
   if (gather) {
     if ((uintptr_t)gather->mc & 15) a.staged = 0;
     for (int r = 0; r < gather->world; r++)

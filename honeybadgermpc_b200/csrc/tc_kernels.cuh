@@ -61,10 +61,11 @@ struct TcArgs {
   unsigned split;
   unsigned half;             // n / 2 of the DFT (split mode)
   unsigned mu;               // floor(2^280 / p)
-  // staged != 0 (needs EW = 16, no gather): results go through shared memory (two buffers of four
+  // staged != 0 (opt-in, needs EW = 16): results go through shared memory (two buffers of four
   // 32-row x 128-byte boxes, XOR-swizzled) so that every global store instruction writes full
-  // 128-byte lines: a warp-wide 32-byte-per-thread store touches 32 lines and costs ~80 cycles of
-  // the SM's store path -- the encode was bound by it.  32 KB of shared memory after the stages.
+  // 128-byte lines instead of one 32-byte sector per thread.  Measured SLOWER than the per-thread
+  // stores on the cfg2 shapes (the extra shared-memory passes and 128-thread barriers cost more
+  // than the store path saves); kept as an option, the tests force both.
   unsigned staged;
   // fused all-gather (hbg_fft_batch_interpolate_allgather): when gather_world > 0 the result of
   // row r is stored at row gather_row0 + r of EVERY rank's buffer -- one multimem.st per 16
@@ -313,6 +314,7 @@ HB_D void tc_fold_reduce(const uint32_t* c, uint32_t mu, Fe& r) {
   for (int i = 0; i < 8; i++) r.w[i] = borrow ? t[i] : u[i];
 }
 
+// one 256-bit store (two 128-bit stores: 21.7 instead of 18.1 us per cfg2 step; .cs: no difference)
 HB_D void tc_st256(uint8_t* p, const Fe& r) {
   asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]),
                "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
@@ -437,9 +439,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
         }
       } else {
-#ifdef TC_B_FIRST  // A/B experiment: the operand ahead of the first tile
-      issue_b();
-#endif
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
         const unsigned s = it % a.stages, ph = (it / a.stages) & 1;
         tc_mbar_wait(&bar_empty[s], ph ^ 1, a.error);
@@ -460,9 +459,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst + kb * 16384),
               "l"(&tmap), "r"((int)(kb * 128)), "r"(row0), "r"(bar)
               : "memory");
-#ifndef TC_B_FIRST
         if (it == 0) issue_b();
-#endif
         TC_TRACE(0, it, 1);
       }
       }
@@ -639,24 +636,20 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&bar_tempty[buf]);
             if (threadIdx.x == 0 && nb < 2) TC_TRACE(2, it, 3 * nb + 2);
-            // both folds first, in one straight line of code: two independent carry-chain streams
-            // for the scheduler to interleave (the epilogue is latency-bound: ~100 instructions per
-            // output at an IPC of ~0.5 per sub-partition); then the two store waves
-            Fe r0, r1;
-            auto fold = [&](const uint32_t* c, Fe& r) {
-              if (PROBE && (hyp & 128)) {  // probe: no arithmetic
-#pragma unroll
-                for (int i = 0; i < 8; i++) r.w[i] = c[i] ^ c[i + 8] ^ c[i + 16] ^ c[i + 24];
-              } else if (narrow)
-                tc_fold_reduce<F, true>(c, a.mu, r);
-              else
-                tc_fold_reduce<F, false>(c, a.mu, r);
-            };
-            if (has0) fold(c0, r0);
-            if (has1) fold(c1, r1);
-            auto wave_body = [&](const Fe& r, bool has, unsigned j) {
+            // (folding both outputs first, to give the scheduler two independent carry-chain streams,
+            // was measured 50 % SLOWER: the two 32-register inputs plus both results exceed the 96
+            // registers a 576-thread CTA gets and the spills land on the critical path)
+            auto wave_body = [&](const uint32_t* c, bool has, unsigned j) {
               const unsigned stg = stg_base + (wave & 1) * 16384;
               if (has) {
+                Fe r;
+                if (PROBE && (hyp & 128)) {  // probe: no arithmetic
+#pragma unroll
+                  for (int i = 0; i < 8; i++) r.w[i] = c[i] ^ c[i + 8] ^ c[i + 16] ^ c[i + 24];
+                } else if (narrow)
+                  tc_fold_reduce<F, true>(c, a.mu, r);
+                else
+                  tc_fold_reduce<F, false>(c, a.mu, r);
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + st_w0), "r"(r.w[0]), "r"(r.w[1]),
                              "r"(r.w[2]), "r"(r.w[3])
                              : "memory");
@@ -687,8 +680,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               }
               wave++;
             };
-            wave_body(r0, has0, 0);
-            if (n_waves > 1) wave_body(r1, has1, 1);
+            wave_body(c0, has0, 0);
+            if (n_waves > 1) wave_body(c1, has1, 1);
             if (threadIdx.x == 0 && nb < 2) TC_TRACE(2, it, 3 * nb + 1);
           }
         }

@@ -288,9 +288,11 @@ int hbg_ctx_set_interp_path(hbg_ctx* ctx, int path);
  * is exceeded the cache is dropped at the entry of the next call (default 256 MB). */
 int hbg_ctx_set_cache_limit(hbg_ctx* ctx, size_t bytes);
 
-/* How the tensor-core kernel writes its results: 0 = transposed through shared memory so that
- * every store instruction writes full 128-byte lines (whenever the output is 16-byte aligned),
- * 1 = one 32-byte store per thread.  Identical bits; the tests force both. */
+/* How the tensor-core kernel writes its results: 0 (default) = one 32-byte store per thread,
+ * 1 = transposed through shared memory so that every store instruction writes full 128-byte
+ * lines (needs 16-byte aligned outputs).  Identical bits; the tests force both.  Measured on the
+ * cfg2 shapes the staged form is the slower one (22.8 vs 18.4 us per step): the two extra
+ * shared-memory passes and the 128-thread barriers cost more than the uncoalesced stores. */
 int hbg_ctx_set_tc_store(hbg_ctx* ctx, int mode);
 
 /* Upper bound on the CTAs (one per SM) a persistent tensor-core launch of this context uses;

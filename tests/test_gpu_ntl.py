@@ -174,12 +174,12 @@ def test_tensor_core_path(ntl):
                 assert ctx.last_kernel() == "tc_apply_kernel", (n, d)
                 # the two store paths of the epilogue (staged full-line stores / 32 bytes per thread)
                 # and a launch confined to a few CTAs (hbg_ctx_set_sm_limit)
-                ctx.set_tc_store("direct")
+                ctx.set_tc_store("staged")
                 ctx.set_sm_limit(3)
                 try:
-                    assert got == ntl.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch, "direct stores")
+                    assert got == ntl.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch, "staged stores")
                 finally:
-                    ctx.set_tc_store("staged")
+                    ctx.set_tc_store("direct")
                     ctx.set_sm_limit(0)
                 ctx.set_matvec_path("no-tc")
                 assert got == ntl.vandermonde_batch_evaluate(xs, polys, P), (n, d, batch)
