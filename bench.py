@@ -200,6 +200,11 @@ def run_cfg5(args, world, rank, local, dev):
     omega = pack_vec([pt.omega.value], P)[0]
     zs = sorted(random.Random(5).sample(range(n), k))
     gather = "auto" if args.gather.startswith("fused") else args.gather  # k = 43: no fused epilogue
+    if gather == "auto" and world >= 3:
+        # cfg5 is bound by its kernels, not by the gather (7x more arithmetic per gathered byte): the
+        # multicast copy kernel, which needs no SMs set aside, beats the bulk-copy default of the
+        # reconstructor at 4 ranks (2.47 against 3.17 ms per pass)
+        gather = "mc"
     rec = ShardedReconstructor(P, omega, pt.order, zs, piece, device=local, depth=2, gather=gather,
                                copy_ctas=args.gather_ctas, parts=parts)
     ctx, stream = rec.ctx, rec.stream
@@ -365,10 +370,32 @@ def run_b200(args):
         ctx.set_tc_store(args.tc_store)
         ctx_enc.set_tc_store(args.tc_store)
     sm_split = None
-    if overlap_encode and args.sm_split > 0:
+    want_split = args.sm_split
+    if want_split < 0:  # auto: N = 1, and the copy-engine gather (a copy KERNEL's SMs would come first)
+        want_split = 0
+        if ((world == 1 or rec.mode == "ce-copy-signal") and overlap_encode
+                and args.matvec_path in ("auto", "tc") and rec.compute_sms == 0):
+            # Persistent tensor-core CTAs own a whole SM, so two full-GPU launches run one after the
+            # other and every launch pays its own pipeline fill on every SM.  Side by side on
+            # disjoint SMs the fills overlap.  Split = argmin over e of the longer chain, in tile
+            # rounds weighted by the per-tile cost ratio (measured); among equals the one closest to
+            # the work-proportional split.  65 536 rows: 104 + 44 SMs (5 and 12 rounds).
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            tiles = (batch + 127) // 128
+            ratio = 2.4  # per-tile cost, encode : interpolate (16 vs 6 outputs; the SM-split sweep in profiles/)
+            ideal = n_sm * ratio / (1.0 + ratio)
+            best = None
+            for e_sm in range(n_sm // 2, n_sm - 8):
+                enc_t = -(-tiles // e_sm) * ratio
+                dec_t = -(-tiles // (n_sm - e_sm)) * 1.0
+                key = (max(enc_t, dec_t), abs(e_sm - ideal))
+                if best is None or key < best[0]:
+                    best = (key, e_sm)
+            want_split = best[1]
+    if overlap_encode and want_split > 0:
         # the two kernels side by side on disjoint SMs instead of one after the other
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        sm_split = [min(args.sm_split, n_sm - 1), n_sm - min(args.sm_split, n_sm - 1)]
+        sm_split = [min(want_split, n_sm - 1), n_sm - min(want_split, n_sm - 1)]
         ctx_enc.set_sm_limit(sm_split[0])
         ctx.set_sm_limit(sm_split[1])
 
@@ -758,9 +785,11 @@ def main():
     ap.add_argument("--sm-limit", type=int, default=0,
                     help="SMs the encode and the interpolation launches may use (0 = all): the rest stay free "
                          "for the gather's copy kernel (N > 1)")
-    ap.add_argument("--sm-split", type=int, default=0,
+    ap.add_argument("--sm-split", type=int, default=-1,
                     help="CTAs (SMs) of the encode launches; the interpolation gets the rest, so that the two "
-                         "persistent kernels of a step run side by side (0 = both use every SM, back to back)")
+                         "persistent kernels of a step run side by side (0 = both use every SM, back to back; "
+                         "-1 = automatic at N = 1 and with the copy-engine gather: the split that balances the "
+                         "two chains)")
     ap.add_argument("--graph-units", type=int, default=4,
                     help="steps per captured graph = lcm(sets, slots) x this (a replay ends with a join of "
                          "all streams, i.e. drains the gather pipeline once)")

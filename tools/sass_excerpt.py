@@ -18,7 +18,7 @@ WANT = ["UTCIMMA", "UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "UTCATOMSWS", "SYNCS"
         "BAR.SYNC", "NANOSLEEP"]
 KERNELS = ["tc_apply_kernel<hb::FieldBLS", "interp_small_kernel<hb::FieldBLS, 6, 64, 2, false, 0>",
            "ntt16_g4_kernel<hb::FieldBLS, 6, 64, false>", "apply_matrix_smem_kernel<hb::FieldBLS>",
-           "ntt_smem_kernel<hb::FieldBLS>", "gather_copy_signal_kernel", "gather_copy_kernel",
+           "ntt_smem_kernel<hb::FieldBLS>", "gather_copy_signal_kernel", "gather_bulk_signal_kernel", "gather_copy_kernel",
            "gather_signal_arrived_kernel", "gather_wait_released_kernel", "gather_wait_kernel",
            "gather_release_kernel", "compare_columns_kernel", "columns_to_rows_kernel",
            "fnt_scale_scatter_kernel<hb::FieldBLS>", "fnt_pointwise_kernel<hb::FieldBLS>",
