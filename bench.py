@@ -37,6 +37,23 @@ UNIT = "shares/s"
 E = 32  # bytes per field element
 
 
+def choose_sm_split(tiles, n_sm, ratio=2.4):
+    """SMs for the encode launches when the two kernels of a step run side by side (the interpolation
+    gets the rest): the split whose longer chain is shortest, in tile rounds weighted by the per-tile
+    cost ratio encode : interpolate (16 vs 6 outputs per row; 2.4 from the sweep in profiles/), and
+    among equals the one closest to the work-proportional split.  65 536 rows on 148 SMs: 104 + 44
+    (5 and 12 rounds)."""
+    ideal = n_sm * ratio / (1.0 + ratio)
+    best = None
+    for e_sm in range(n_sm // 2, n_sm - 8):
+        enc_t = -(-tiles // e_sm) * ratio
+        dec_t = -(-tiles // (n_sm - e_sm)) * 1.0
+        key = (max(enc_t, dec_t), abs(e_sm - ideal))
+        if best is None or key < best[0]:
+            best = (key, e_sm)
+    return best[1]
+
+
 def synth(batch, width, seed):
     """uniform in [0, 2^254) subset of [0, p): canonical residues as uint64[batch,width,4]"""
     import numpy as np
@@ -381,17 +398,7 @@ def run_b200(args):
             # rounds weighted by the per-tile cost ratio (measured); among equals the one closest to
             # the work-proportional split.  65 536 rows: 104 + 44 SMs (5 and 12 rounds).
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-            tiles = (batch + 127) // 128
-            ratio = 2.4  # per-tile cost, encode : interpolate (16 vs 6 outputs; the SM-split sweep in profiles/)
-            ideal = n_sm * ratio / (1.0 + ratio)
-            best = None
-            for e_sm in range(n_sm // 2, n_sm - 8):
-                enc_t = -(-tiles // e_sm) * ratio
-                dec_t = -(-tiles // (n_sm - e_sm)) * 1.0
-                key = (max(enc_t, dec_t), abs(e_sm - ideal))
-                if best is None or key < best[0]:
-                    best = (key, e_sm)
-            want_split = best[1]
+            want_split = choose_sm_split((batch + 127) // 128, n_sm)
     if overlap_encode and want_split > 0:
         # the two kernels side by side on disjoint SMs instead of one after the other
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -534,6 +541,7 @@ def run_b200(args):
     # 10 us the gaps between a recorded event and the next launch reaching the GPU are inside the
     # interval.  The per-kernel durations the roofline uses therefore come from two more graphs, one
     # kernel each, `unit` launches back to back on the bench stream, timed as a whole.
+    full_ms = {}
     if not args.no_graph:
         try:
             scratch = torch.empty_like(c[0])
@@ -559,6 +567,19 @@ def run_b200(args):
             dec_ms = chain_ms(lambda s_: ctx.fft_batch_interpolate(omega, pt.order, ZS, y_ptr[s_], batch,
                                                                    scratch.data_ptr(), _native.MEM_DEVICE))
             assert torch.equal(scratch, c[(unit - 1) % sets]), "interpolation chain: wrong result"
+            if sm_split:
+                # the same two chains with every SM available: the kernels as such, next to the kernels
+                # as the timed region runs them (each on its share of the SMs)
+                ctx_enc.set_sm_limit(0)
+                ctx.set_sm_limit(0)
+                ctx_enc.set_stream(stream.cuda_stream)
+                full_ms["encode"] = chain_ms(encode)
+                ctx_enc.set_stream(enc_stream.cuda_stream)
+                full_ms["interpolate"] = chain_ms(
+                    lambda s_: ctx.fft_batch_interpolate(omega, pt.order, ZS, y_ptr[s_], batch, scratch.data_ptr(),
+                                                         _native.MEM_DEVICE))
+                ctx_enc.set_sm_limit(sm_split[0])
+                ctx.set_sm_limit(sm_split[1])
             kernel_src = (f"two CUDA graphs of {unit} back-to-back launches of one kernel each on the bench stream, "
                           "rotating buffer sets, CUDA events around 4 replays (launch gaps inside a chain "
                           "included); `kernel_ms_eager` = the per-launch event brackets of an eager pass")
@@ -605,6 +626,8 @@ def run_b200(args):
                 "kernel": f"{dom}: {names[dom]}", "peak_source": peak_src,
                 "kernel_ms": {"encode": enc_ms, "interpolate": dec_ms}, "kernels": names,
                 "kernel_ms_source": kernel_src, "kernel_ms_eager": eager_ms,
+                "kernel_ms_all_sms": full_ms or None,
+                "frac_all_sms": (dom_bytes / (full_ms[dom] * 1e-3) / 1e9 / peak) if full_ms else None,
                 "step_GBps": (enc_bytes + dec_bytes) / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": (enc_bytes + dec_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
                 "tensor": {"u8_mac_per_s": macs[dom] * batch / (dom_ms * 1e-3),
@@ -651,39 +674,51 @@ def run_b200(args):
 
     # ---- end to end: the C-ABI call a reference-side binding makes, HOST buffers
     # (pinned), H2D + kernel + D2H inside the timed region
-    e2e_steps = max(3, min(args.steps, 60))
+    e2e_steps = max(4, min(args.steps, 60))
     hc = torch.from_numpy(synth(batch, K, 0xE2E + rank).view(np.int64)).pin_memory()
-    he = torch.empty((batch, N_PARTIES, 4), dtype=torch.int64).pin_memory()
     hy = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
-    hr = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
+    # two sets of output buffers: the results of step i are waited for (hbg_ctx_wait_pending) while the
+    # transfers of step i+1 are in flight, and a set is only written again after it has been waited for
+    he = [torch.empty((batch, N_PARTIES, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
+    hr = [torch.empty((batch, K, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
 
-    def e2e_step():
-        ctx.fft_batch_evaluate(omega, pt.order, hc.data_ptr(), batch, K, N_PARTIES, he.data_ptr(),
+    def e2e_step(b):
+        ctx.fft_batch_evaluate(omega, pt.order, hc.data_ptr(), batch, K, N_PARTIES, he[b].data_ptr(),
                                _native.MEM_HOST)
-        ctx.fft_batch_interpolate(omega, pt.order, ZS, hy.data_ptr(), batch, hr.data_ptr(),
+        ctx.fft_batch_interpolate(omega, pt.order, ZS, hy.data_ptr(), batch, hr[b].data_ptr(),
                                   _native.MEM_HOST)
 
-    e2e_step()
-    hy.copy_(he[:, ZS, :])
-    # asynchronous host mode: the two calls of a step overlap on the PCIe link; every step
-    # ends with hbg_ctx_synchronize, i.e. with its results readable in host memory
+    e2e_limit = ctx_enc is not ctx and sm_split is not None
+    if e2e_limit:
+        ctx.set_sm_limit(0)  # one context, one stream: its launches take every SM
+    e2e_step(0)
+    hy.copy_(he[0][:, ZS, :])
+    # asynchronous host mode: the two calls of a step overlap on the PCIe link, and so do consecutive
+    # steps (H2D of the next under the D2H of the current: the D2H side, 46 of the 71 MB, is the floor)
     ctx.set_host_async(True)
-    for _ in range(2):
-        e2e_step()
-        ctx.synchronize()
+    for i in range(2):
+        e2e_step(i)
+    ctx.synchronize()
+    for b in range(2):
+        he[b].zero_()
+        hr[b].zero_()
     barrier()
     t0 = time.perf_counter()
     marks = [t0]
-    for _ in range(e2e_steps):
-        e2e_step()
-        ctx.synchronize()
+    for i in range(e2e_steps):
+        e2e_step(i & 1)
+        ctx.wait_pending(2)  # step i-1 (two calls) is complete in host memory
         marks.append(time.perf_counter())
+    ctx.synchronize()
     torch.cuda.synchronize()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
     per_step = sorted(b - a for a, b in zip(marks, marks[1:]))
     ctx.set_host_async(False)
-    assert torch.equal(hr, hc), "end-to-end round trip mismatch"
-    assert torch.equal(he[:, ZS, :], hy), "end-to-end encode mismatch"
+    if e2e_limit:
+        ctx.set_sm_limit(sm_split[1])
+    for b in range(2):
+        assert torch.equal(hr[b], hc), "end-to-end round trip mismatch"
+        assert torch.equal(he[b][:, ZS, :], hy), "end-to-end encode mismatch"
     if world > 1:
         tt = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -695,7 +730,9 @@ def run_b200(args):
            "ms_per_step_min_median_max": [per_step[0] * 1e3, per_step[len(per_step) // 2] * 1e3,
                                           per_step[-1] * 1e3],
            "boundary": "hbg_fft_batch_evaluate + hbg_fft_batch_interpolate, HBG_MEM_HOST, pinned buffers, "
-                       "host_async on, hbg_ctx_synchronize at the end of every step"}
+                       "host_async on; after enqueueing step i the host waits for step i-1 "
+                       "(hbg_ctx_wait_pending(ctx, 2)): every step's outputs are complete in host memory "
+                       "before its buffers are reused, two output buffer sets"}
 
     cfg5 = None
     if args.cfg5 == "on" or (args.cfg5 == "auto" and args.batch == 65536):

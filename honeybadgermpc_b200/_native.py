@@ -93,6 +93,7 @@ SIGNATURES = {
          ctypes.c_int]),
     "hbg_ctx_set_cache_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "hbg_ctx_set_sm_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "hbg_ctx_wait_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_ctx_set_tc_store": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_ctx_set_interp_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "hbg_ctx_set_wb_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -284,6 +285,10 @@ class Context:
     def set_tc_store(self, mode):
         """"direct" (default: 32 bytes per thread) or "staged" (through shared memory, full 128-byte lines)"""
         self._check(self.lib.hbg_ctx_set_tc_store(self.handle, {"direct": 0, "staged": 1}[mode]))
+
+    def wait_pending(self, keep):
+        """host_async: wait until at most `keep` of the latest host-buffer calls are in flight"""
+        self._check(self.lib.hbg_ctx_wait_pending(self.handle, int(keep)))
 
     def set_sm_limit(self, ctas):
         """At most `ctas` CTAs (= SMs) per tensor-core launch of this context; 0 = all."""

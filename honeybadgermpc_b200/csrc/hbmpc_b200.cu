@@ -1509,6 +1509,22 @@ int hbg_ctx_synchronize(hbg_ctx* ctx) {
   return HBG_OK;
 }
 
+int hbg_ctx_wait_pending(hbg_ctx* ctx, int keep) {
+  if (!ctx) return HBG_ERR_INVALID;
+  if (keep < 0 || keep > 3) return fail(ctx, HBG_ERR_INVALID, "0 <= keep <= 3 (the pipeline has four slots)");
+  if (!ctx->s_out) return HBG_OK;  // no host-buffer call yet
+  // calls are numbered by next_slot; the newest is next_slot - 1: everything older than the
+  // newest `keep` must have drained (D2H complete: its outputs are readable in host memory)
+  for (unsigned j = (unsigned)keep; j < 4 && j < ctx->next_slot; j++) {
+    hbg_ctx::HostSlot& sl = ctx->slots[(ctx->next_slot - 1 - j) % 4];
+    if (sl.used) {
+      CU(cudaEventSynchronize(sl.done));
+      sl.used = false;
+    }
+  }
+  return HBG_OK;
+}
+
 int hbg_ctx_set_host_async(hbg_ctx* ctx, int on) {
   if (!ctx) return HBG_ERR_INVALID;
   if (!on && ctx->host_async) {

@@ -75,6 +75,30 @@ def sharded_apply(fn, rows, group=None):
     return all_gather_rows(fn(rows[lo:hi]), rows.shape[0], group)
 
 
+def gather_mode(gather, world, multicast):
+    """The transport behind ``gather=`` for ``world`` ranks (``multicast``: the symmetric-memory
+    allocation has an NVSwitch multicast address).  ``"auto"`` follows the measurements
+    (profiles/r2_gather_modes_n4.txt, r2g_*): 2 ranks -- copy engines (30 us per cfg2 step; copy
+    kernels 38-57); 3-4 ranks -- the unicast TMA bulk-copy kernel on 16 SMs the compute kernels leave
+    free (70 us at 4 ranks; multicast kernel 83, copy engines 95: unicast receives world-1 blocks, a
+    multicast store world -- the sender's own block comes back through the switch); 5 ranks and more
+    -- the multicast kernel (154 us at 8, copy engines 238: one block leaves the GPU instead of
+    seven), or the bulk-copy kernel where there is no multicast address."""
+    if gather == "auto":
+        if world <= 2:
+            return "ce-copy-signal"
+        if world <= 4 or not multicast:
+            return "bulk-copy-signal"
+        return "multimem-copy-signal"
+    return {"ce": "ce-copy-signal",
+            "mc": "multimem-copy-signal" if multicast else "p2p-copy-signal",
+            "p2p": "p2p-copy-signal",
+            "bulk": "bulk-copy-signal",
+            "fused": "fused-multimem-signal" if multicast else "fused-p2p-signal",
+            "fused-barrier": "fused-multimem" if multicast else "fused-p2p",
+            "copy": "multimem-copy" if multicast else "p2p-copy"}[gather]
+
+
 class ShardedReconstructor:
     """One rank of a batch-sharded ``fft_batch_interpolate`` whose decoded blocks
     are all-gathered on every rank.
@@ -169,25 +193,7 @@ class ShardedReconstructor:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(self.group)  # every rank's flags are zero before anyone signals
                 mc = int(getattr(self.handles[0], "multicast_ptr", 0) or 0)
-                # measured (profiles/r2_scale_*, r2_gather_modes_n4): at 2 ranks the copy engines win
-                # (36 vs 57 us per cfg2 step); at 3-4 ranks the unicast TMA copy kernel on 16 SMs the
-                # compute kernels leave free (72 us at 4 ranks, multicast kernel 83, copy engines 95:
-                # unicast receives world-1 blocks, a multicast store world -- the sender's own block
-                # comes back through the switch); from 5 ranks on the multicast kernel (154 us at 8,
-                # copy engines 238: one block leaves the GPU instead of seven)
-                if self.world <= 2 or not mc:
-                    auto = "ce-copy-signal"
-                elif self.world <= 4:
-                    auto = "bulk-copy-signal"
-                else:
-                    auto = "multimem-copy-signal"
-                self.mode = {"auto": auto, "ce": "ce-copy-signal",
-                             "mc": "multimem-copy-signal" if mc else "p2p-copy-signal",
-                             "p2p": "p2p-copy-signal",
-                             "bulk": "bulk-copy-signal",
-                             "fused": "fused-multimem-signal" if mc else "fused-p2p-signal",
-                             "fused-barrier": "fused-multimem" if mc else "fused-p2p",
-                             "copy": "multimem-copy" if mc else "p2p-copy"}[gather]
+                self.mode = gather_mode(gather, self.world, bool(mc))
             except Exception as exc:  # noqa: BLE001 - no symmetric memory on this build / fabric
                 self.fallback_reason = repr(exc)
                 self.handles, self.gathered, self.mode = [], [], "nccl"

@@ -73,6 +73,12 @@ int hbg_ctx_synchronize(hbg_ctx* ctx);
  * the PCIe link (H2D of one under D2H of the previous).  Host buffers should be
  * pinned for the copies to be asynchronous. */
 int hbg_ctx_set_host_async(hbg_ctx* ctx, int on);
+/* With host_async on: block until at most `keep` (0..3) of the most recent host-buffer calls of
+ * this context are still in flight; the outputs of all earlier calls are then complete in host
+ * memory.  keep = 0 is hbg_ctx_synchronize for the host pipeline.  Lets a caller read the
+ * results of open i while the transfers of open i+1 run (PCIe is full duplex and the D2H side
+ * is the longer one: 46 of the 71 MB of a cfg2 step). */
+int hbg_ctx_wait_pending(hbg_ctx* ctx, int keep);
 /* Number of kernels this context has launched so far. */
 uint64_t hbg_ctx_launch_count(const hbg_ctx* ctx);
 /* Name of the dominant kernel of the last batch call (for bench.py / profiles). */

@@ -61,3 +61,19 @@ def test_b200_arm_needs_a_device():
     res = run(["--steps", "1", "--warmup", "1", "--no-cpu"])
     assert res.returncode != 0
     assert "no CPU fallback" in res.stderr
+
+
+def test_sm_split_choice():
+    """the automatic --sm-split: balanced chains, the documented 104 + 44 at the headline size"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.choose_sm_split(512, 148) == 104
+    for tiles, n_sm in ((512, 148), (8192, 148), (100, 148), (512, 132), (1, 148)):
+        e = bench.choose_sm_split(tiles, n_sm)
+        assert n_sm // 2 <= e < n_sm - 8
+        # no neighbouring split has a shorter longer-chain
+        cost = lambda x: max(-(-tiles // x) * 2.4, -(-tiles // (n_sm - x)) * 1.0)  # noqa: E731
+        assert all(cost(e) <= cost(x) for x in range(n_sm // 2, n_sm - 8))

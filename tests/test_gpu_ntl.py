@@ -409,6 +409,22 @@ def test_host_async_mode(ntl):
         ctx.set_host_async(False)
     for o, w in zip(outs, want):
         assert np.array_equal(o, w)
+    # hbg_ctx_wait_pending: after enqueueing call i, every call older than the newest `keep` is
+    # complete in host memory -- checked call by call while later calls are still in flight
+    outs = [np.zeros((batch, n, 4), dtype=np.uint64) for _ in cs]
+    ctx.set_host_async(True)
+    try:
+        for i, (c, o) in enumerate(zip(cs, outs)):
+            ctx.fft_batch_evaluate(omega, pt.order, c, batch, k, n, o)
+            ctx.wait_pending(2)
+            if i >= 2:
+                assert np.array_equal(outs[i - 2], want[i - 2]), i
+        ctx.wait_pending(0)
+        assert np.array_equal(outs[-1], want[-1]) and np.array_equal(outs[-2], want[-2])
+        with pytest.raises(Exception):
+            ctx.wait_pending(4)
+    finally:
+        ctx.set_host_async(False)
 
 
 def test_c_abi_error_paths(ntl):

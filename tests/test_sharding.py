@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 
 sys.path.insert(0, ROOT)
-from honeybadgermpc_b200.sharding import all_gather_rows, shard_bounds, sharded_apply  # noqa: E402
+from honeybadgermpc_b200.sharding import all_gather_rows, gather_mode, shard_bounds, sharded_apply  # noqa: E402
 
 
 def test_shard_bounds_cover_the_batch():
@@ -24,6 +24,21 @@ def test_shard_bounds_cover_the_batch():
                 assert b == c and a <= b
             per = -(-batch // world) if batch else 0
             assert all(hi - lo <= per for lo, hi in blocks)
+
+
+def test_gather_mode_policy():
+    """which transport `gather="auto"` picks per world size, with and without a multicast address"""
+    assert gather_mode("auto", 2, True) == gather_mode("auto", 2, False) == "ce-copy-signal"
+    assert gather_mode("auto", 3, True) == gather_mode("auto", 4, False) == "bulk-copy-signal"
+    assert gather_mode("auto", 8, True) == "multimem-copy-signal"
+    assert gather_mode("auto", 8, False) == "bulk-copy-signal"
+    for name in ("ce", "mc", "p2p", "bulk", "fused", "fused-barrier", "copy"):
+        for mc in (True, False):
+            mode = gather_mode(name, 4, mc)
+            assert ("multimem" in mode) <= mc, (name, mc, mode)  # multimem modes need the address
+            assert mode.endswith("signal") == (name not in ("fused-barrier", "copy"))
+    with pytest.raises(KeyError):
+        gather_mode("bogus", 2, True)
 
 
 def _free_port():
