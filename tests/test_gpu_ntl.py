@@ -203,6 +203,18 @@ def test_tensor_core_path(ntl):
         got = ntl.unpack_rows(ntl.vandermonde_batch_interpolate_limbs(xl, raw, P))
         want = orc.vandermonde_batch_interpolate(xs, [[v % P for v in row] for row in ntl.unpack_rows(raw)], P)
         assert got == want
+        # the narrow fold of the epilogue at its limit (K = 256 bytes: d = 8; every input byte 0xFF
+        # makes the column sums as large as they get) and the first shape of the wide fold (d = 9)
+        for d in (8, 9):
+            xs = rng.sample(range(1, 1 << 30), d)
+            raw = np.full((300, d, 4), 2 ** 64 - 1, dtype=np.uint64)
+            raw[1::3] = rng.getrandbits(63)
+            got = ntl.unpack_rows(ntl.vandermonde_batch_interpolate_limbs(ntl.pack_vec(xs, P), raw, P))
+            assert ctx.last_kernel() == "tc_apply_kernel"
+            rows = [0, 1, 2, 128, 299]
+            want = orc.vandermonde_batch_interpolate(
+                xs, [[v % P for v in row] for row in ntl.unpack_rows(raw[rows])], P)
+            assert [got[i] for i in rows] == want, d
     finally:
         ctx.set_matvec_path("auto")
 
