@@ -19,7 +19,7 @@
 //   * D = A * B^T is one tcgen05.mma.kind::i8 chain per 128-row tile (u8 x u8 -> s32 in
 //     TMEM); the epilogue reads each output's 32 column sums with tcgen05.ld, carries
 //     them into a 288-bit integer and reduces it with one small-quotient Barrett step
-//     (q < 2^26: 8 IMAD.WIDE) and one conditional subtraction.  No Montgomery form
+//     (q < 2^26) and one conditional subtraction (tc_fold_reduce).  No Montgomery form
 //     anywhere: inputs, constants and outputs are plain residues.
 //
 // Warp roles of the persistent CTA (one per SM): EW = 8, 12 or 16 epilogue warps (TMEM
@@ -28,10 +28,13 @@
 // copies (128-byte-wide boxes, SWIZZLE_128B = the UMMA K-major swizzled layout; rows past the
 // batch and bytes past K are zero-filled by the TMA unit; measured: 16-byte cp.async copies
 // from 128 threads could not keep more than ~2 TB/s of loads in flight), one warp owns
-// TMEM and issues the MMAs
-// (one elected thread).  The constant operand is fetched once per CTA by one TMA bulk
-// copy and stays resident in shared memory; accumulators ping-pong between two
-// 256-column TMEM buffers so the MMAs of one block overlap the epilogue of the previous.
+// TMEM and issues the MMAs (warp-uniform loops, one elected lane issues).  The constant operand
+// is fetched once per CTA -- one TMA bulk copy per 8-output block, queued behind the first input
+// tile -- and stays resident in shared memory; accumulators ping-pong between two 256-column
+// TMEM buffers, and an epilogue warp hands a buffer back as soon as its TMEM reads have landed,
+// before the arithmetic, so the MMAs of one block overlap the epilogue of the previous.
+// What bounds it (tools/tmem_probe.cu, tools/tc_probe.cu): the ~100-instruction
+// epilogue per output and, for large batches, the write side of HBM; not the MMAs, not TMEM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
