@@ -65,6 +65,72 @@ def synth(batch, width, seed):
     return a
 
 
+def gpu_numa_cpus(props):
+    """(NUMA node, its CPUs) of the GPU with these device properties, from sysfs; (None, None)
+    when the platform does not say (single node, container without /sys, node -1)."""
+    try:
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None, None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = parse_cpulist(fh.read())
+        return node, (cpus or None)
+    except (OSError, ValueError, AttributeError):
+        return None, None
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> {0, 1, 2, 3, 8, 10, 11}"""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+class numa_local:
+    """Run a block with the calling thread confined to the CPUs of the GPU's NUMA node: pinned host
+    buffers allocated inside are first touched there, and the thread that enqueues the copies stays
+    next to them.  No-op where the node is unknown.  The previous affinity is restored on exit (the
+    CPU baseline counts its threads from the affinity mask)."""
+
+    def __init__(self, props):
+        self.node, cpus = gpu_numa_cpus(props)
+        self.saved = None
+        try:
+            allowed = os.sched_getaffinity(0)
+        except (AttributeError, OSError):
+            allowed = None
+        self.cpus = (cpus & allowed) if (cpus and allowed) else None
+        self.applied = False
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+                self.applied = True
+            except OSError:
+                self.applied = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.applied and self.saved:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
+
+    def describe(self):
+        return {"gpu_numa_node": self.node, "cpus_used": len(self.cpus) if self.applied else None,
+                "applied": self.applied}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU while the timed region runs."""
 
@@ -674,51 +740,55 @@ def run_b200(args):
 
     # ---- end to end: the C-ABI call a reference-side binding makes, HOST buffers
     # (pinned), H2D + kernel + D2H inside the timed region
-    e2e_steps = max(4, min(args.steps, 60))
-    hc = torch.from_numpy(synth(batch, K, 0xE2E + rank).view(np.int64)).pin_memory()
-    hy = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
-    # two sets of output buffers: the results of step i are waited for (hbg_ctx_wait_pending) while the
-    # transfers of step i+1 are in flight, and a set is only written again after it has been waited for
-    he = [torch.empty((batch, N_PARTIES, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
-    hr = [torch.empty((batch, K, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
+    # the pinned buffers and the enqueueing thread of the end-to-end leg live on the GPU's NUMA node
+    # (8 ranks on one host: every rank's 71 MB per step crosses the socket interconnect otherwise)
+    numa = numa_local(torch.cuda.get_device_properties(dev))
+    with numa:
+        e2e_steps = max(4, min(args.steps, 60))
+        hc = torch.from_numpy(synth(batch, K, 0xE2E + rank).view(np.int64)).pin_memory()
+        hy = torch.empty((batch, K, 4), dtype=torch.int64).pin_memory()
+        # two sets of output buffers: the results of step i are waited for (hbg_ctx_wait_pending) while the
+        # transfers of step i+1 are in flight, and a set is only written again after it has been waited for
+        he = [torch.empty((batch, N_PARTIES, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
+        hr = [torch.empty((batch, K, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
 
-    def e2e_step(b):
-        ctx.fft_batch_evaluate(omega, pt.order, hc.data_ptr(), batch, K, N_PARTIES, he[b].data_ptr(),
-                               _native.MEM_HOST)
-        ctx.fft_batch_interpolate(omega, pt.order, ZS, hy.data_ptr(), batch, hr[b].data_ptr(),
-                                  _native.MEM_HOST)
+        def e2e_step(b):
+            ctx.fft_batch_evaluate(omega, pt.order, hc.data_ptr(), batch, K, N_PARTIES, he[b].data_ptr(),
+                                   _native.MEM_HOST)
+            ctx.fft_batch_interpolate(omega, pt.order, ZS, hy.data_ptr(), batch, hr[b].data_ptr(),
+                                      _native.MEM_HOST)
 
-    e2e_limit = ctx_enc is not ctx and sm_split is not None
-    if e2e_limit:
-        ctx.set_sm_limit(0)  # one context, one stream: its launches take every SM
-    e2e_step(0)
-    hy.copy_(he[0][:, ZS, :])
-    # asynchronous host mode: the two calls of a step overlap on the PCIe link, and so do consecutive
-    # steps (H2D of the next under the D2H of the current: the D2H side, 46 of the 71 MB, is the floor)
-    ctx.set_host_async(True)
-    for i in range(2):
-        e2e_step(i)
-    ctx.synchronize()
-    for b in range(2):
-        he[b].zero_()
-        hr[b].zero_()
-    barrier()
-    t0 = time.perf_counter()
-    marks = [t0]
-    for i in range(e2e_steps):
-        e2e_step(i & 1)
-        ctx.wait_pending(2)  # step i-1 (two calls) is complete in host memory
-        marks.append(time.perf_counter())
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    per_step = sorted(b - a for a, b in zip(marks, marks[1:]))
-    ctx.set_host_async(False)
-    if e2e_limit:
-        ctx.set_sm_limit(sm_split[1])
-    for b in range(2):
-        assert torch.equal(hr[b], hc), "end-to-end round trip mismatch"
-        assert torch.equal(he[b][:, ZS, :], hy), "end-to-end encode mismatch"
+        e2e_limit = ctx_enc is not ctx and sm_split is not None
+        if e2e_limit:
+            ctx.set_sm_limit(0)  # one context, one stream: its launches take every SM
+        e2e_step(0)
+        hy.copy_(he[0][:, ZS, :])
+        # asynchronous host mode: the two calls of a step overlap on the PCIe link, and so do consecutive
+        # steps (H2D of the next under the D2H of the current: the D2H side, 46 of the 71 MB, is the floor)
+        ctx.set_host_async(True)
+        for i in range(2):
+            e2e_step(i)
+        ctx.synchronize()
+        for b in range(2):
+            he[b].zero_()
+            hr[b].zero_()
+        barrier()
+        t0 = time.perf_counter()
+        marks = [t0]
+        for i in range(e2e_steps):
+            e2e_step(i & 1)
+            ctx.wait_pending(2)  # step i-1 (two calls) is complete in host memory
+            marks.append(time.perf_counter())
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        e2e_dt = (time.perf_counter() - t0) / e2e_steps
+        per_step = sorted(b - a for a, b in zip(marks, marks[1:]))
+        ctx.set_host_async(False)
+        if e2e_limit:
+            ctx.set_sm_limit(sm_split[1])
+        for b in range(2):
+            assert torch.equal(hr[b], hc), "end-to-end round trip mismatch"
+            assert torch.equal(he[b][:, ZS, :], hy), "end-to-end encode mismatch"
     if world > 1:
         tt = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -729,6 +799,7 @@ def run_b200(args):
            "ms_per_step": e2e_dt * 1e3,
            "ms_per_step_min_median_max": [per_step[0] * 1e3, per_step[len(per_step) // 2] * 1e3,
                                           per_step[-1] * 1e3],
+           "numa": numa.describe(),
            "boundary": "hbg_fft_batch_evaluate + hbg_fft_batch_interpolate, HBG_MEM_HOST, pinned buffers, "
                        "host_async on; after enqueueing step i the host waits for step i-1 "
                        "(hbg_ctx_wait_pending(ctx, 2)): every step's outputs are complete in host memory "

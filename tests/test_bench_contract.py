@@ -77,3 +77,24 @@ def test_sm_split_choice():
         # no neighbouring split has a shorter longer-chain
         cost = lambda x: max(-(-tiles // x) * 2.4, -(-tiles // (n_sm - x)) * 1.0)  # noqa: E731
         assert all(cost(e) <= cost(x) for x in range(n_sm // 2, n_sm - 8))
+
+
+def test_numa_helpers():
+    """sysfs parsing of the e2e leg's NUMA pinning; unknown topology is a no-op that restores affinity"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert bench.parse_cpulist("5") == {5} and bench.parse_cpulist("") == set()
+
+    class NoSuchGpu:
+        pci_domain_id, pci_bus_id, pci_device_id = 0xFFFF, 0xFE, 0x1F
+
+    assert bench.gpu_numa_cpus(NoSuchGpu) == (None, None)
+    before = os.sched_getaffinity(0)
+    pin = bench.numa_local(NoSuchGpu)
+    with pin:
+        assert os.sched_getaffinity(0) == before
+    assert os.sched_getaffinity(0) == before and pin.describe()["applied"] is False
