@@ -57,6 +57,7 @@ struct hbg_ctx {
   unsigned* gather_counter = nullptr;  // last-CTA detection of gather_copy_signal_kernel
   cudaStream_t copy_streams[7] = {};   // hbg_allgather_block_ce: one stream per peer, so the copies run
   cudaEvent_t copy_fork = nullptr, copy_join[7] = {};  // on different copy engines concurrently
+  int ce_pieces = 1;                   // pieces per peer block in hbg_allgather_block_ce (HBMPC_CE_PIECES)
   int interp_arith = 0; // arithmetic of the small-k kernel when the path is auto / 3
   int interp_path = 0;  // fft_batch_interpolate: 0 auto, 1 V^-1 matrix, 2 NTT-structured (fnt_decode_step2)
   std::string err;
@@ -1426,6 +1427,10 @@ int hbg_ctx_create(hbg_ctx** out, const uint64_t modulus[4], int device) {
       cudaMemset(ctx->gather_counter, 0, 2 * sizeof(unsigned)) != cudaSuccess)
     ctx->gather_counter = nullptr;
   if (count > 1) {  // multi-GPU box: the per-peer copy streams of hbg_allgather_block_ce
+    if (const char* e = getenv("HBMPC_CE_PIECES")) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= 7) ctx->ce_pieces = v;
+    }
     bool ok = cudaEventCreateWithFlags(&ctx->copy_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 7 && ok; i++)
       ok = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -1769,14 +1774,31 @@ int hbg_allgather_block_ce(hbg_ctx* ctx, const void* block, size_t bytes, void* 
   // fork: one copy per peer, each on its own stream (= its own copy engine), then join
   if (world > 1 && !ctx->copy_fork) return fail(ctx, HBG_ERR_CUDA, "copy streams were not created");
   if (world > 1) CU(cudaEventRecord(ctx->copy_fork, ctx->stream));
+  // One copy engine moves ~570 GB/s of a 770 GB/s link (22 us for 12.6 MB).  Cutting a peer's block
+  // into pieces on several streams (= engines; HBMPC_CE_PIECES, up to 7 streams in all, pieces of at
+  // least 1 MB) was measured SLOWER at 2 ranks -- 29.2 / 31.6 / 34.7 / 38.8 us per cfg2 step for
+  // 1 / 2 / 3 / 4 pieces (profiles/r2g_ce_pieces_n2.jsonl): every extra copy is another engine
+  // switch between kernels -- so the default is one copy per peer.
+  int pieces = world > 1 ? 7 / (world - 1) : 1;
+  if (pieces > ctx->ce_pieces) pieces = ctx->ce_pieces;
+  while (pieces > 1 && bytes / (size_t)pieces < ((size_t)1 << 20)) pieces--;
+  if (pieces < 1) pieces = 1;
+  const size_t per = ((bytes / (size_t)pieces) + 255) & ~(size_t)255;
+  int sidx = 0;
   for (int i = 1; i < world; i++) {
     const int r = (rank + i) % world;  // staggered: at any moment the ranks target different peers
     if (!peer_out[r]) return fail(ctx, HBG_ERR_INVALID, "null peer pointer");
-    cudaStream_t cs = ctx->copy_streams[i - 1];
-    CU(cudaStreamWaitEvent(cs, ctx->copy_fork, 0));
-    CU(cudaMemcpyAsync((uint8_t*)peer_out[r] + offset_bytes, block, bytes, cudaMemcpyDeviceToDevice, cs));
-    CU(cudaEventRecord(ctx->copy_join[i - 1], cs));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_join[i - 1], 0));
+    for (int pc = 0; pc < pieces; pc++, sidx++) {
+      const size_t o = (size_t)pc * per;
+      if (o >= bytes) break;
+      const size_t len = bytes - o < per || pc == pieces - 1 ? bytes - o : per;
+      cudaStream_t cs = ctx->copy_streams[sidx];
+      CU(cudaStreamWaitEvent(cs, ctx->copy_fork, 0));
+      CU(cudaMemcpyAsync((uint8_t*)peer_out[r] + offset_bytes + o, (const uint8_t*)block + o, len,
+                         cudaMemcpyDeviceToDevice, cs));
+      CU(cudaEventRecord(ctx->copy_join[sidx], cs));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_join[sidx], 0));
+    }
   }
   gather_signal_arrived_kernel<<<1, 32, 0, ctx->stream>>>(s);
   CU(cudaGetLastError());
