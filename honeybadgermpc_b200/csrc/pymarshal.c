@@ -74,8 +74,36 @@ PyObject* hbg_py_pack_rows(PyObject* rows, Py_ssize_t width, PyObject* p_obj, un
   Py_RETURN_NONE;
 }
 
+/* 32 little-endian bytes -> int.  _PyLong_FromByteArray walks the value byte by byte (~90 ns per
+ * 256-bit element, the largest single cost of unpacking a big batch); from CPython 3.12 on
+ * _PyLong_FromDigits takes the 30-bit digits directly, which four 64-bit limbs yield with a few
+ * shifts.  Same value either way (tests/test_marshal.py compares both on edge cases). */
+static PyObject* long_from_le32(const unsigned char* in) {
+#if PY_VERSION_HEX >= 0x030C0000 && PYLONG_BITS_IN_DIGIT == 30
+  unsigned long long l[4];
+  memcpy(l, in, 32); /* little-endian host (x86-64 / aarch64) */
+  digit d[9];
+  for (int k = 0; k < 9; k++) {
+    const int bit = 30 * k, limb = bit >> 6, off = bit & 63;
+    unsigned long long v = l[limb] >> off;
+    if (off > 34 && limb < 3) v |= l[limb + 1] << (64 - off);
+    d[k] = (digit)(v & 0x3fffffffULL);
+  }
+  Py_ssize_t n = 9;
+  while (n > 0 && d[n - 1] == 0) n--;
+  return (PyObject*)_PyLong_FromDigits(0, n, d);
+#else
+  return _PyLong_FromByteArray(in, 32, 1, 0);
+#endif
+}
+
+/* for the tests: the two conversions side by side on one 32-byte value */
+PyObject* hbg_py_long_from_le32(const unsigned char* in, int reference) {
+  return reference ? _PyLong_FromByteArray(in, 32, 1, 0) : long_from_le32(in);
+}
+
 /* in[batch][width][32] -> list of `batch` lists of `width` ints */
-PyObject* hbg_py_unpack_rows(const unsigned char* in, Py_ssize_t batch, Py_ssize_t width) {
+static PyObject* unpack_rows_inner(const unsigned char* in, Py_ssize_t batch, Py_ssize_t width) {
   PyObject* outer = PyList_New(batch);
   if (!outer) return NULL;
   for (Py_ssize_t i = 0; i < batch; i++) {
@@ -85,7 +113,7 @@ PyObject* hbg_py_unpack_rows(const unsigned char* in, Py_ssize_t batch, Py_ssize
       return NULL;
     }
     for (Py_ssize_t j = 0; j < width; j++) {
-      PyObject* v = _PyLong_FromByteArray(in + ((size_t)i * width + j) * 32, 32, 1, 0);
+      PyObject* v = long_from_le32(in + ((size_t)i * width + j) * 32);
       if (!v) {
         Py_DECREF(row);
         Py_DECREF(outer);
@@ -96,6 +124,19 @@ PyObject* hbg_py_unpack_rows(const unsigned char* in, Py_ssize_t batch, Py_ssize
     PyList_SET_ITEM(outer, i, row);
   }
   return outer;
+}
+
+PyObject* hbg_py_unpack_rows(const unsigned char* in, Py_ssize_t batch, Py_ssize_t width) {
+  /* tens of thousands of row lists allocated in one go trigger a young-generation collection
+   * every 700 of them, none of which can free anything: pause the collector for the loop */
+#if PY_VERSION_HEX >= 0x030A0000
+  const int was_enabled = PyGC_Disable();
+  PyObject* r = unpack_rows_inner(in, batch, width);
+  if (was_enabled) PyGC_Enable();
+  return r;
+#else
+  return unpack_rows_inner(in, batch, width);
+#endif
 }
 
 /* Offset of a __slots__ member of a class, or -1 with an exception set. */
@@ -128,12 +169,22 @@ PyObject* hbg_py_wrap_elements(const unsigned char* in, Py_ssize_t count, PyObje
   if (ov < 0 || of < 0 || om < 0) return NULL;
   PyObject* out = PyList_New(count);
   if (!out) return NULL;
+  /* the allocations below count towards the collector's young-generation threshold although
+   * every element is untracked at once: pause it for the loop (see hbg_py_unpack_rows) */
+#if PY_VERSION_HEX >= 0x030A0000
+  const int gc_was_enabled = PyGC_Disable();
+#else
+  const int gc_was_enabled = 0;
+#endif
   for (Py_ssize_t i = 0; i < count; i++) {
-    PyObject* v = _PyLong_FromByteArray(in + (size_t)i * 32, 32, 1, 0);
+    PyObject* v = long_from_le32(in + (size_t)i * 32);
     PyObject* e = v ? tp->tp_alloc(tp, 0) : NULL;
     if (!e) {
       Py_XDECREF(v);
       Py_DECREF(out);
+#if PY_VERSION_HEX >= 0x030A0000
+      if (gc_was_enabled) PyGC_Enable();
+#endif
       return NULL;
     }
     /* An element refers to an int and to its (immortal, per-modulus) field object: it can never
@@ -149,5 +200,8 @@ PyObject* hbg_py_wrap_elements(const unsigned char* in, Py_ssize_t count, PyObje
     *(PyObject**)((char*)e + om) = modulus;
     PyList_SET_ITEM(out, i, e);
   }
+#if PY_VERSION_HEX >= 0x030A0000
+  if (gc_was_enabled) PyGC_Enable();
+#endif
   return out;
 }

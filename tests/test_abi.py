@@ -100,6 +100,31 @@ def test_c_marshalling_matches_python():
             ntl.pack_rows(bad, 1, P)
 
 
+def test_c_long_construction_matches_cpython():
+    """pymarshal.c builds 256-bit ints from 30-bit digits (_PyLong_FromDigits, CPython >= 3.12):
+    same objects as _PyLong_FromByteArray on digit-boundary values, zero, and random widths --
+    value, hash, bit_length, arithmetic and str (which walk the digits) all agree"""
+    import ctypes
+    import random
+
+    graft.build_marshal()
+    lib = ctypes.PyDLL(os.path.join(ROOT, "honeybadgermpc_b200", "libhbmpc_pymarshal.so"))
+    lib.hbg_py_long_from_le32.restype = ctypes.py_object
+    lib.hbg_py_long_from_le32.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    rng = random.Random(5)
+    vals = [0, 1, 2, 255, 256, 2 ** 256 - 1, 2 ** 255, P, P - 1]
+    for k in range(1, 9):  # around every 30-bit digit boundary and every 64-bit limb boundary
+        for base in (2 ** (30 * k), 2 ** (64 * min(k, 3))):
+            vals += [base - 1, base, base + 1]
+    vals += [rng.getrandbits(rng.randrange(1, 257)) for _ in range(5000)]
+    for v in vals:
+        b = v.to_bytes(32, "little")
+        fast, ref = lib.hbg_py_long_from_le32(b, 0), lib.hbg_py_long_from_le32(b, 1)
+        assert type(fast) is int and fast == ref == v, v
+        assert hash(fast) == hash(v) and fast.bit_length() == v.bit_length() and str(fast) == str(v)
+        assert fast + 1 == v + 1 and fast * fast == v * v and (fast >> 31) == (v >> 31) and -fast == -v
+
+
 def test_host_marshalling_round_trip():
     from honeybadgermpc_b200.ntl import pack_rows, unpack_rows
 
