@@ -18,6 +18,36 @@ static int ge_le32(const unsigned char* a, const unsigned char* b) {
   return 1;
 }
 
+#if PY_VERSION_HEX >= 0x030C0000 && PYLONG_BITS_IN_DIGIT == 30
+/* A non-negative int below 2^256 -> 32 little-endian bytes straight from its 30-bit digits
+ * (CPython >= 3.12 layout, cpython/longintrepr.h); 0 when the value needs the general path
+ * (negative: the caller raises; >= 2^256: reduced mod p there). */
+static int fast_le32(PyObject* v, unsigned char* out) {
+  const PyLongObject* lv = (const PyLongObject*)v;
+  const uintptr_t tag = lv->long_value.lv_tag;
+  if ((tag & _PyLong_SIGN_MASK) == 2) return 0;
+  const Py_ssize_t nd = (Py_ssize_t)(tag >> _PyLong_NON_SIZE_BITS);
+  if (nd > 9) return 0;
+  unsigned long long l[4] = {0, 0, 0, 0};
+  if ((tag & _PyLong_SIGN_MASK) != 1) { /* not zero */
+    for (Py_ssize_t k = 0; k < nd; k++) {
+      const unsigned long long d = lv->long_value.ob_digit[k];
+      const int bit = 30 * (int)k, limb = bit >> 6, off = bit & 63;
+      l[limb] |= d << off;
+      if (off > 34) {
+        const unsigned long long hi = d >> (64 - off);
+        if (limb < 3)
+          l[limb + 1] |= hi;
+        else if (hi)
+          return 0; /* >= 2^256 */
+      }
+    }
+  }
+  memcpy(out, l, 32); /* little-endian host */
+  return 1;
+}
+#endif
+
 /* one element -> 32 bytes, reduced mod p; returns 0, or -1 with an exception set */
 static int pack_one(PyObject* v, PyObject* p_obj, const unsigned char* p_le, unsigned char* out) {
   if (!PyLong_Check(v)) {
@@ -28,6 +58,11 @@ static int pack_one(PyObject* v, PyObject* p_obj, const unsigned char* p_le, uns
     PyErr_SetString(PyExc_OverflowError, "can't convert negative int to unsigned");
     return -1;
   }
+#if PY_VERSION_HEX >= 0x030C0000 && PYLONG_BITS_IN_DIGIT == 30
+  if (fast_le32(v, out)) {
+    if (!ge_le32(out, p_le)) return 0;
+  } else
+#endif
   if (_PyLong_NumBits(v) <= 256) {
     if (_PyLong_AsByteArray((PyLongObject*)v, out, 32, 1, 0) < 0) return -1;
     if (!ge_le32(out, p_le)) return 0;

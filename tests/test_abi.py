@@ -90,6 +90,11 @@ def test_c_marshalling_matches_python():
     rng = random.Random(5)
     rows = [[rng.randrange(P) for _ in range(rng.randint(0, 7))] for _ in range(200)]
     rows += [[0, 1, P - 1, P, 2 * P + 5, 2 ** 300 + 7], (3, 4, 5), [True]]
+    # the digit-level fast path of pack_one: every 30-bit digit and 64-bit limb boundary, the
+    # 256-bit edge (values >= 2^256 and >= p take the general path and are reduced)
+    rows += [[2 ** (30 * k) - 1, 2 ** (30 * k), 2 ** (30 * k) + 1] for k in range(1, 10)]
+    rows += [[2 ** (64 * k) - 1, 2 ** (64 * k), 2 ** (64 * k) + 1] for k in range(1, 5)]
+    rows += [[2 ** 255, 2 ** 256 - 1, 2 ** 256, 2 ** 256 + P, (1 << 256) - P, 2 ** 269, 2 ** 270]]
     for width in (0, 1, 4, 7):
         a = ntl.pack_rows(rows, width, P)
         assert np.array_equal(a, ntl._pack_rows_py(rows, width, P))
