@@ -126,6 +126,7 @@ static PyObject* long_from_le32(const unsigned char* in) {
   }
   Py_ssize_t n = 9;
   while (n > 0 && d[n - 1] == 0) n--;
+  if (n <= 1) return PyLong_FromUnsignedLong(n ? (unsigned long)d[0] : 0ul); /* small ints stay the cached ones */
   return (PyObject*)_PyLong_FromDigits(0, n, d);
 #else
   return _PyLong_FromByteArray(in, 32, 1, 0);
