@@ -23,7 +23,7 @@ import numpy as np
 
 from . import reed_solomon as rs
 from .field import GF
-from .ntl import pack_rows, unpack_rows, wrap_elements
+from .ntl import pack_elements, pack_rows, unpack_rows, wrap_elements
 from .polynomial import EvalPoint
 from .utils import gc_paused, subscribe_recv
 
@@ -105,11 +105,13 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     of a pickled int list.  All parties of a run must use the same format."""
     timing = logging.LoggerAdapter(logging.getLogger("benchmark_logger"), {"node_id": myid})
     k = (t if degree is None else degree) + 1
-    with gc_paused():
-        values = [share.value for share in secret_shares]
+    if not isinstance(secret_shares, (list, tuple)):
+        secret_shares = list(secret_shares)  # the reference iterates once (:127); any iterable works
+    count = len(secret_shares)
+    values = None  # only the fault-injection hook needs the Python ints
     if config is not None and config.induce_faults:  # fault injection hook of the reference (:129-131)
         logging.debug("[FAULT][BatchReconstruction] Sending random shares.")
-        values = [random.randint(0, p - 1) for _ in values]
+        values = [random.randint(0, p - 1) for _ in range(count)]
 
     inbox = _Inbox(recv, n)
     field = GF(p)
@@ -118,12 +120,12 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
     codec = (rs.EncoderFactory.get(point, kind), rs.DecoderFactory.get(point, kind),
              rs.RobustDecoderFactory.get(
                  t, point, algorithm=rs.Algorithm.GAO if config is None else config.decoding_algorithm))
-    if not values:
+    if not count:
         # unreachable from Mpc (open_share_array returns early on empty arrays, mpc.py:175-177); the
         # reference fails here too (chunk_data([]) gives a flat list, utils/misc.py:40-41)
         inbox.close()
         raise TypeError("batch_reconstruct needs at least one share")
-    n_chunks = -(-len(values) // k)  # chunk polynomials of k coefficients, the last zero padded
+    n_chunks = -(-count // k)  # chunk polynomials of k coefficients, the last zero padded
 
     async def decode_round(tag):
         started = time.time()
@@ -146,7 +148,9 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
         # chunk_data + encode + transpose_lists of the reference (:158-167) on limb arrays: the flat
         # share list is packed once (zero padded to n_chunks * k), reshaped into the chunk
         # polynomials, encoded, and transposed per destination before any Python list is made
-        coeffs = pack_rows([values], n_chunks * k, p)[0].reshape(n_chunks, k, 4)
+        flat = (pack_elements(secret_shares, n_chunks * k, p) if values is None
+                else pack_rows([values], n_chunks * k, p)[0])
+        coeffs = flat.reshape(n_chunks, k, 4)
         encoded = codec[0].encode_batch_limbs(coeffs)                        # [chunks][n][4]
         by_dest = np.ascontiguousarray(encoded.transpose(1, 0, 2))           # [n][chunks][4]
         outgoing = [by_dest[j].tobytes() for j in range(n)] if wire == "limbs" else unpack_rows(by_dest)
@@ -173,6 +177,6 @@ async def batch_reconstruct(secret_shares, p, t, n, myid, send, recv, config=Non
 
     inbox.close()
     opened = secrets.reshape(-1, 4)  # uint64[chunks * k, 4]: the coefficient rows, flattened
-    assert opened.shape[0] >= len(values)
+    assert opened.shape[0] >= count
     with gc_paused():
-        return wrap_elements(opened[: len(values)], field)
+        return wrap_elements(opened[:count], field)

@@ -189,6 +189,53 @@ static Py_ssize_t slot_offset(PyObject* cls, const char* name) {
   return off;
 }
 
+/* elems: sequence of objects with an int attribute `value` (GFElement: read from its slot; any
+ * other object: getattr) -> out[width][32], reduced mod p, zero padded to `width`.  The inverse of
+ * hbg_py_wrap_elements: what batch_reconstruct does with its input shares
+ * ([share.value for share in shares] + pack in one pass).  Returns None. */
+PyObject* hbg_py_pack_elements(PyObject* elems, Py_ssize_t width, PyObject* cls, PyObject* p_obj,
+                               unsigned char* out) {
+  unsigned char p_le[32];
+  if (!PyLong_Check(p_obj) || _PyLong_AsByteArray((PyLongObject*)p_obj, p_le, 32, 1, 0) < 0) {
+    if (!PyErr_Occurred()) PyErr_SetString(PyExc_TypeError, "modulus must be an int below 2**256");
+    return NULL;
+  }
+  if (!PyType_Check(cls)) {
+    PyErr_SetString(PyExc_TypeError, "cls must be a class");
+    return NULL;
+  }
+  const Py_ssize_t ov = slot_offset(cls, "value");
+  if (ov < 0) return NULL;
+  PyObject* seq = PySequence_Fast(elems, "shares must be a sequence");
+  if (!seq) return NULL;
+  const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+  const Py_ssize_t upto = n < width ? n : width;
+  for (Py_ssize_t i = 0; i < upto; i++) {
+    PyObject* e = PySequence_Fast_GET_ITEM(seq, i);
+    int rc;
+    if (Py_TYPE(e) == (PyTypeObject*)cls) {
+      PyObject* v = *(PyObject**)((char*)e + ov);
+      if (!v) {
+        PyErr_SetString(PyExc_AttributeError, "value");
+        rc = -1;
+      } else {
+        rc = pack_one(v, p_obj, p_le, out + (size_t)i * 32);
+      }
+    } else {
+      PyObject* v = PyObject_GetAttrString(e, "value");
+      rc = v ? pack_one(v, p_obj, p_le, out + (size_t)i * 32) : -1;
+      Py_XDECREF(v);
+    }
+    if (rc < 0) {
+      Py_DECREF(seq);
+      return NULL;
+    }
+  }
+  if (upto < width) memset(out + (size_t)upto * 32, 0, (size_t)(width - upto) * 32);
+  Py_DECREF(seq);
+  Py_RETURN_NONE;
+}
+
 /* in[count][32] (canonical residues) -> list of `count` instances of `cls`, a class with the
  * slots (value, field, modulus) -- GFElement -- built without running its __init__:
  * value = the int, field / modulus = the given objects.  What batch_reconstruct returns;

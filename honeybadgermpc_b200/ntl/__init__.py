@@ -110,6 +110,9 @@ def _load_marshal():
                                          ctypes.c_void_p]
         lib.hbg_py_unpack_rows.restype = ctypes.py_object
         lib.hbg_py_unpack_rows.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_ssize_t]
+        lib.hbg_py_pack_elements.restype = ctypes.py_object
+        lib.hbg_py_pack_elements.argtypes = [ctypes.py_object, ctypes.c_ssize_t, ctypes.py_object,
+                                             ctypes.py_object, ctypes.c_void_p]
         lib.hbg_py_wrap_elements.restype = ctypes.py_object
         lib.hbg_py_wrap_elements.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.py_object,
                                              ctypes.py_object, ctypes.py_object]
@@ -142,6 +145,18 @@ def unpack_rows(arr):
         return _unpack_rows_py(arr)
     arr = np.ascontiguousarray(arr)
     return _marshal.hbg_py_unpack_rows(arr.ctypes.data, arr.shape[0], arr.shape[1])
+
+
+def pack_elements(elements, width, p):
+    """sequence of field elements (objects with an int ``value``) -> uint64[width, 4], reduced mod p
+    and zero padded: ``pack_rows([[e.value for e in elements]], width, p)[0]`` in one C pass."""
+    if _marshal is None:
+        return _pack_rows_py([[e.value for e in elements]], width, p)[0]
+    from ..field import GFElement
+
+    out = np.empty((width, 4), dtype=np.uint64)
+    _marshal.hbg_py_pack_elements(elements, width, GFElement, p, out.ctypes.data)
+    return out
 
 
 def wrap_elements(arr, field):

@@ -42,6 +42,8 @@ class DecodeValidationError(HoneyBadgerMPCError):
 def _canonical(col, p):
     """every row of uint64[rows, 4] is < p"""
     pl = [(p >> (64 * i)) & (2 ** 64 - 1) for i in range(4)]
+    if pl[3] and bool((col[:, 3] < np.uint64(pl[3])).all()):
+        return True  # decided by the top limb alone (all but ~2^-64 of the canonical residues of a 255-bit p)
     lt = np.zeros(col.shape[0], dtype=bool)
     eq = np.ones(col.shape[0], dtype=bool)
     for i in (3, 2, 1, 0):

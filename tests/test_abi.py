@@ -141,6 +141,44 @@ def test_host_marshalling_round_trip():
         pack_rows([[-1]], 1, P)
 
 
+def test_c_element_packing_matches_python():
+    """hbg_py_pack_elements: [e.value for e in shares] + pack_rows in one pass -- GFElement slots,
+    foreign objects with a `value` attribute, reduction mod p, padding, truncation, errors"""
+    import random
+
+    import numpy as np
+
+    graft.build_marshal()
+    import importlib
+
+    import honeybadgermpc_b200.ntl as ntl
+    from honeybadgermpc_b200.field import GF
+
+    ntl = importlib.reload(ntl)
+    assert ntl._marshal is not None
+    field = GF(P)
+    rng = random.Random(3)
+
+    class Foreign:
+        def __init__(self, v):
+            self.value = v
+
+    elems = [field(rng.randrange(P)) for _ in range(300)] + [Foreign(7), Foreign(P + 3), Foreign(2 ** 300), field(0)]
+    want = ntl._pack_rows_py([[e.value for e in elems]], len(elems) + 5, P)[0]
+    assert np.array_equal(ntl.pack_elements(elems, len(elems) + 5, P), want)       # zero padded
+    assert np.array_equal(ntl.pack_elements(tuple(elems), 10, P), want[:10])       # truncated, any sequence
+    assert ntl.pack_elements([], 3, P).tolist() == [[0] * 4] * 3
+    with pytest.raises(AttributeError):
+        ntl.pack_elements([object()], 1, P)
+    with pytest.raises(OverflowError):
+        ntl.pack_elements([Foreign(-1)], 1, P)
+    saved, ntl._marshal = ntl._marshal, None
+    try:
+        assert np.array_equal(ntl.pack_elements(elems, len(elems) + 5, P), want)
+    finally:
+        ntl._marshal = saved
+
+
 def test_c_element_wrapping_matches_python():
     """hbg_py_wrap_elements (csrc/pymarshal.c) builds the same GFElement objects as the
     Python constructor; the pure-Python fallback of ntl.wrap_elements agrees"""
