@@ -83,6 +83,12 @@ def test_live_reference_three_way(monkeypatch):
             assert d.run_trace(d.ours_decoder(s), s) == ref, f"ours, schedule {seed}"
             ends[ref[-1][0]] = ends.get(ref[-1][0], 0) + 1
         assert ends.get("raise", 0) > 10  # the exception paths are exercised
+        # party counts the schedule generator does not draw by itself (t = 4, 7, 10)
+        for n in (13, 22, 31):
+            for seed in range(30000, 30020):
+                s = d.make_schedule(seed, n=n, field="bls")
+                ref = d.run_trace(d.reference_decoder(s), s)
+                assert d.run_trace(d.ours_decoder(s), s) == ref, f"ours, n={n}, schedule {seed}"
     finally:
         logging.disable(logging.NOTSET)
 
